@@ -1,0 +1,168 @@
+/*
+ * seq2kminmers.h -- C ABI of the B200-native sequence -> k-min-mer path.
+ *
+ * This is the drop-in boundary for rchikhi/rust-seq2kminmers' hot path.  Each entry point
+ * cites the reference interface it replaces (file:line into the reference crate).  The
+ * reference exposes a per-sequence iterator,
+ *
+ *     KminmersIterator::new(seq:&[u8], l, k, density:f64, mode:HashMode) -> io::Result<Self>   src/lib.rs:89
+ *     impl Iterator for KminmersIterator { type Item = KminmerHash; fn next() }                src/lib.rs:179-270
+ *     KminmerHash { hash:u64, start:usize, end:usize, offset:usize, rev:bool }                 src/kminmer.rs:128-135
+ *
+ * and the replacement is a BATCHED form of it: many sequences per call, results returned as
+ * structure-of-arrays in the same per-sequence order the iterator would yield them.
+ * `offset` (index of the k-min-mer inside its sequence) is implicit: item i of sequence r has
+ * offset = i - km_off[r].
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Nothing unwinds across this ABI:
+ * every call returns an int status (0 = ok, negative = error, see S2K_ERR_*).
+ *
+ * Precedent inside the reference for an opaque-handle C ABI: src/nthash_c.rs:7-29.
+ */
+#ifndef SEQ2KMINMERS_H
+#define SEQ2KMINMERS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2K_ABI_VERSION 1
+
+/* HashMode, src/lib.rs:21-27 (same discriminant order). */
+typedef enum s2k_hash_mode {
+    S2K_MODE_REGULAR = 0,  /* scalar ntHash1-32 in original space (nthash32 crate, src/lib.rs:108,217-229) */
+    S2K_MODE_HPC     = 1,  /* scalar fused HPC + ntHash1-32 (src/nthash_hpc.rs) */
+    S2K_MODE_SIMD    = 2,  /* AVX-512 ntHash semantics in original space (src/nthash_avx512_32.rs) */
+    S2K_MODE_HPCSIMD = 3   /* AVX-512 HPC then AVX-512 ntHash (src/hpc.rs + src/nthash_hpc_simd.rs) */
+} s2k_hash_mode;
+
+/* Which rolling hash.  NT1_32 is what src/lib.rs compiles; NT2_31 is the 31-bit hybrid of
+ * src/nthash2_avx512_32.rs (commented out of the reference build, src/lib.rs:8-9) and is only
+ * defined for the SIMD modes, whose iterator it would replace. */
+typedef enum s2k_hash_variant {
+    S2K_HASH_NT1_32 = 0,
+    S2K_HASH_NT2_31 = 1
+} s2k_hash_variant;
+
+/* Status codes.  The reference panics (unwrap/assert) where these are returned:
+ *   S2K_ERR_L_TOO_BIG   assert!(k<=31) src/nthash_avx512_32.rs:33; KSizeTooBig / assert!(k<256) src/nthash_hpc.rs:123-133
+ *   S2K_ERR_BAD_PARAM   l==0 or k==0 (usize underflow panics in src/lib.rs:238-247), unknown mode/variant
+ * Sequences with len <= l are not errors: they yield nothing (src/lib.rs:97). */
+#define S2K_OK                0
+#define S2K_ERR_BAD_PARAM    -1
+#define S2K_ERR_L_TOO_BIG    -2
+#define S2K_ERR_CUDA         -3
+#define S2K_ERR_OOM          -4
+#define S2K_ERR_BAD_OFFSETS  -5   /* seq_off[0] != 0, decreasing offsets, or a sequence of >= 2^32 bases */
+#define S2K_ERR_INTERNAL     -6   /* device-side consistency check failed */
+#define S2K_ERR_NULL         -7
+
+/* Arguments of KminmersIterator::new after `seq` (src/lib.rs:89). */
+typedef struct s2k_params {
+    uint32_t l;        /* minimizer length */
+    uint32_t k;        /* k-min-mer length (minimizers per window) */
+    double   density;  /* FH = f64, src/lib.rs:34 */
+    int32_t  mode;     /* s2k_hash_mode */
+    int32_t  variant;  /* s2k_hash_variant */
+} s2k_params;
+
+/* One universe minimizer: the item of NtHashHPCIterator / NtHashHPCSIMDIterator
+ * (start, end, hash) -- src/nthash_hpc.rs:193, src/nthash_hpc_simd.rs:59 -- plus the index of the
+ * sequence it belongs to.  start/end are in ORIGINAL coordinates of that sequence. */
+typedef struct s2k_minimizer {
+    uint32_t hash;
+    uint32_t start;
+    uint32_t end;
+    uint32_t seq;
+} s2k_minimizer;
+
+#define S2K_LOC_HOST   0
+#define S2K_LOC_DEVICE 1
+
+/* Result of one batched run.  All pointers are owned by the context and stay valid until the next
+ * s2k_run / s2k_run_device call on it or s2k_ctx_destroy.  `location` says whether they are host (pinned) or device
+ * pointers.  Items of sequence r are [km_off[r], km_off[r+1]) in iterator order. */
+typedef struct s2k_result {
+    uint64_t n_seqs;
+    uint64_t n_items;                /* k-min-mers (KminmerHash items) over the whole batch */
+    uint64_t n_minimizers;           /* universe minimizers over the whole batch (before the simd tail rule) */
+    const uint64_t *hash;            /* [n_items]  KminmerHash.hash  */
+    const uint32_t *start;           /* [n_items]  KminmerHash.start */
+    const uint32_t *end;             /* [n_items]  KminmerHash.end   */
+    const uint8_t  *rev;             /* [n_items]  KminmerHash.rev   */
+    const uint64_t *km_off;          /* [n_seqs+1] exclusive prefix of per-sequence item counts */
+    const s2k_minimizer *minimizers; /* [n_minimizers] ordered minimizer stream (device runs; NULL for host runs
+                                        unless S2K_WANT_MINIMIZERS was set) */
+    const uint64_t *min_off;         /* [n_seqs+1] exclusive prefix of per-sequence minimizer counts (same rule) */
+    const uint32_t *min_cnt;         /* [n_seqs]   minimizers per sequence that feed the window stage (i.e. after the
+                                        `(len-l+1) % 16 == 0` tail rule of src/nthash_avx512_32.rs:134-138) */
+    int32_t location;
+    int32_t reserved;
+} s2k_result;
+
+typedef struct s2k_ctx s2k_ctx;
+
+/* Flags for s2k_ctx_set_flags. */
+#define S2K_WANT_MINIMIZERS 1u  /* s2k_run (host) also copies the minimizer stream back */
+
+/* Lifetime.  One context = one CUDA device + one stream + grow-only device/pinned buffers.
+ * A context is single-threaded (like one KminmersIterator, src/main.rs:65-79); distinct contexts may be
+ * used concurrently from distinct host threads; multi-GPU = one context per device. */
+int  s2k_ctx_create(int device, s2k_ctx **out);
+void s2k_ctx_destroy(s2k_ctx *ctx);
+int  s2k_ctx_set_flags(s2k_ctx *ctx, uint32_t flags);
+
+/* KminmersIterator::new + collect over a batch, HOST buffers (src/lib.rs:89, 179-270).
+ *   bases   : concatenated sequences, ASCII, seq_off[n_seqs] bytes
+ *   seq_off : n_seqs+1 offsets, seq_off[0]==0, non-decreasing
+ * Includes H2D of inputs and D2H of results; result pointers are pinned host memory. */
+int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs,
+            const s2k_params *params, s2k_result *out);
+
+/* Same, DEVICE buffers already resident in HBM (bases 16-byte aligned); results stay on the device.
+ * `stream` is a cudaStream_t (NULL = the context's own stream).  Returns after the launch sequence has been
+ * enqueued and the two scalar totals have been read back (one stream synchronisation). */
+int s2k_run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs,
+                   uint64_t n_bases, const s2k_params *params, void *stream, s2k_result *out);
+
+/* encode_rle_simd over a batch (src/hpc.rs:44-147): homopolymer-compressed bytes and the run-start index of
+ * each kept byte (relative to its sequence), plus per-sequence offsets into both.  Host buffers in, pinned
+ * host pointers out (valid until the next call on the context). */
+typedef struct s2k_rle_result {
+    uint64_t n_seqs;
+    uint64_t n_hpc;            /* total kept bytes */
+    const uint8_t  *hpc;       /* [n_hpc] */
+    const uint32_t *pos;       /* [n_hpc] run starts, original coordinates inside the sequence */
+    const uint64_t *hpc_off;   /* [n_seqs+1] */
+    int32_t location;
+    int32_t reserved;
+} s2k_rle_result;
+int s2k_encode_rle(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs,
+                   s2k_rle_result *out);
+
+/* Selection bounds exactly as the reference derives them (src/lib.rs:91, src/nthash_avx512_32.rs:47-48,
+ * src/nthash2_avx512_32.rs:52-54). */
+void s2k_bounds(double density, uint32_t *bound_scalar, uint32_t *bound_simd, uint32_t *bound_31);
+
+/* Pinned host memory for callers that want s2k_run's H2D copies to run at full PCIe rate. */
+int  s2k_host_alloc(size_t bytes, void **out);
+void s2k_host_free(void *p);
+
+/* Diagnostics. */
+const char *s2k_last_error(const s2k_ctx *ctx);
+const char *s2k_strerror(int status);
+int s2k_abi_version(void);
+/* Kernels launched by the context since creation (for benchmark bookkeeping). */
+uint64_t s2k_launch_count(const s2k_ctx *ctx);
+/* Name and average duration (ms) of the context's dominant kernel over the last s2k_run_device call,
+ * measured with CUDA events on the launching stream when timing is enabled. */
+int s2k_ctx_set_timing(s2k_ctx *ctx, int enabled);
+int s2k_last_kernel_ms(const s2k_ctx *ctx, double *minimizer_ms, double *window_ms, uint32_t *minimizer_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQ2KMINMERS_H */

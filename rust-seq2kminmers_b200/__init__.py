@@ -1,0 +1,399 @@
+"""rust-seq2kminmers_b200 -- B200-native sequence -> k-min-mer path, host-side mirror of the reference API.
+
+The reference crate exposes (src/lib.rs:5-39, 70-132, 179-270; src/kminmer.rs:128-177):
+
+    KminmersIterator::new(seq, l, k, density, mode) -> Iterator<Item = KminmerHash>
+    HashMode::{Regular, Hpc, Simd, HpcSimd}
+    KminmerHash { hash, start, end, offset, rev }            (equality/order on .hash only)
+    NtHashHPCIterator / NtHashSIMDIterator / NtHashHPCSIMDIterator   -> (start, end, hash) minimizers
+    hpc(), encode_rle(), encode_rle_simd()
+
+This module keeps those names and argument meanings on top of the C ABI in include/seq2kminmers.h
+(libs2k_b200.so: hand-written CUDA for sm_100a).  There is NO CPU implementation here: if the CUDA library
+is missing or no GPU is present, constructing a Context raises.  (The directory name contains a hyphen, as
+the reference crate's does; import it with importlib.import_module("rust-seq2kminmers_b200") or through the
+`seq2kminmers_b200` alias module at the repository root.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Iterator, Optional, Sequence
+
+import numpy as np
+
+__all__ = [
+    "HashMode", "HashVariant", "KminmerHash", "Kminmer", "KminmersIterator", "KminmersBatch", "Context", "Library",
+    "S2KError", "NtHashHPCIterator", "NtHashSIMDIterator", "NtHashHPCSIMDIterator", "hpc", "encode_rle",
+    "encode_rle_simd", "bounds", "default_library", "LIB_PATH",
+]
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libs2k_b200.so"
+HEADER_PATH = PKG_DIR.parent / "include" / "seq2kminmers.h"
+
+
+class HashMode(enum.IntEnum):
+    """src/lib.rs:21-27."""
+    Regular = 0
+    Hpc = 1
+    Simd = 2
+    HpcSimd = 3
+
+
+class HashVariant(enum.IntEnum):
+    """NT1_32: src/nthash_avx512_32.rs / src/nthash_hpc.rs; NT2_31: src/nthash2_avx512_32.rs."""
+    NT1_32 = 0
+    NT2_31 = 1
+
+
+class S2KError(RuntimeError):
+    """Raised where the reference panics (unwrap/assert) or on a CUDA failure; carries the C status code."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"s2k status {status}: {message}")
+        self.status = status
+
+
+class _Params(C.Structure):
+    _fields_ = [("l", C.c_uint32), ("k", C.c_uint32), ("density", C.c_double), ("mode", C.c_int32),
+                ("variant", C.c_int32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("n_items", C.c_uint64), ("n_minimizers", C.c_uint64),
+                ("hash", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p), ("rev", C.c_void_p),
+                ("km_off", C.c_void_p), ("minimizers", C.c_void_p), ("min_off", C.c_void_p), ("min_cnt", C.c_void_p),
+                ("location", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _RleResult(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("n_hpc", C.c_uint64), ("hpc", C.c_void_p), ("pos", C.c_void_p),
+                ("hpc_off", C.c_void_p), ("location", C.c_int32), ("reserved", C.c_int32)]
+
+
+MINIMIZER_DTYPE = np.dtype([("hash", "<u4"), ("start", "<u4"), ("end", "<u4"), ("seq", "<u4")])
+
+# every symbol include/seq2kminmers.h declares
+ABI_SYMBOLS = (
+    "s2k_ctx_create", "s2k_ctx_destroy", "s2k_ctx_set_flags", "s2k_run", "s2k_run_device", "s2k_encode_rle",
+    "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
+    "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms",
+)
+
+
+class Library:
+    """The C ABI, loaded from a shared object.  The default is the nvcc-built product library."""
+
+    def __init__(self, path: Optional[Path] = None):
+        self.path = Path(path) if path else LIB_PATH
+        if not self.path.exists():
+            raise ImportError(
+                f"{self.path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback for this path.")
+        self.c = L = C.CDLL(str(self.path))
+        vp = C.c_void_p
+        L.s2k_ctx_create.restype = C.c_int
+        L.s2k_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.s2k_ctx_destroy.restype = None
+        L.s2k_ctx_destroy.argtypes = [vp]
+        L.s2k_ctx_set_flags.restype = C.c_int
+        L.s2k_ctx_set_flags.argtypes = [vp, C.c_uint32]
+        L.s2k_run.restype = C.c_int
+        L.s2k_run.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(_Params), C.POINTER(_Result)]
+        L.s2k_run_device.restype = C.c_int
+        L.s2k_run_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(_Params), vp, C.POINTER(_Result)]
+        L.s2k_encode_rle.restype = C.c_int
+        L.s2k_encode_rle.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(_RleResult)]
+        L.s2k_bounds.restype = None
+        L.s2k_bounds.argtypes = [C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.s2k_host_alloc.restype = C.c_int
+        L.s2k_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        L.s2k_host_free.restype = None
+        L.s2k_host_free.argtypes = [vp]
+        L.s2k_last_error.restype = C.c_char_p
+        L.s2k_last_error.argtypes = [vp]
+        L.s2k_strerror.restype = C.c_char_p
+        L.s2k_strerror.argtypes = [C.c_int]
+        L.s2k_abi_version.restype = C.c_int
+        L.s2k_abi_version.argtypes = []
+        L.s2k_launch_count.restype = C.c_uint64
+        L.s2k_launch_count.argtypes = [vp]
+        L.s2k_ctx_set_timing.restype = C.c_int
+        L.s2k_ctx_set_timing.argtypes = [vp, C.c_int]
+        L.s2k_last_kernel_ms.restype = C.c_int
+        L.s2k_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+
+
+_default: Optional[Library] = None
+
+
+def default_library() -> Library:
+    global _default
+    if _default is None:
+        _default = Library()
+    return _default
+
+
+def bounds(density: float, lib: Optional[Library] = None):
+    """(bound_scalar, bound_simd, bound_31) -- src/lib.rs:91, src/nthash_avx512_32.rs:47-48, nthash2:52-54."""
+    lib = lib or default_library()
+    a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib.c.s2k_bounds(float(density), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def _view(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.empty(0, dtype=dtype)
+    dt = np.dtype(dtype)
+    buf = (C.c_uint8 * (count * dt.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=count)
+
+
+@dataclass
+class KminmersBatch:
+    """SoA result of one batched run (host copies).  Items of sequence r: [km_off[r], km_off[r+1])."""
+    n_seqs: int
+    hash: np.ndarray      # u64 [n_items]
+    start: np.ndarray     # u32
+    end: np.ndarray       # u32
+    rev: np.ndarray       # u8
+    km_off: np.ndarray    # u64 [n_seqs+1]
+    min_off: np.ndarray   # u64 [n_seqs+1]
+    min_cnt: np.ndarray   # u32 [n_seqs]
+    n_minimizers: int
+    minimizers: Optional[np.ndarray] = None   # MINIMIZER_DTYPE [n_minimizers]
+
+    @property
+    def n_items(self) -> int:
+        return int(self.hash.shape[0])
+
+    def items(self, r: int) -> Iterator["KminmerHash"]:
+        a, b = int(self.km_off[r]), int(self.km_off[r + 1])
+        for i in range(a, b):
+            yield KminmerHash(int(self.hash[i]), int(self.start[i]), int(self.end[i]), i - a, bool(self.rev[i]))
+
+    def minimizers_of(self, r: int) -> np.ndarray:
+        """Minimizers of sequence r that feed the window stage (what the reference's inner iterator yields)."""
+        if self.minimizers is None:
+            raise ValueError("run with want_minimizers=True")
+        a = int(self.min_off[r])
+        return self.minimizers[a:a + int(self.min_cnt[r])]
+
+
+@dataclass(frozen=True)
+class KminmerHash:
+    """src/kminmer.rs:128-135; equality and order by `hash` only (src/kminmer.rs:181-203)."""
+    hash: int
+    start: int
+    end: int
+    offset: int
+    rev: bool
+
+    def get_hash(self) -> int:   # trait Kminmer, src/kminmer.rs:12-15
+        return self.hash
+
+    def __eq__(self, other):
+        return isinstance(other, KminmerHash) and self.hash == other.hash
+
+    def __lt__(self, other):
+        return self.hash < other.hash
+
+    def __hash__(self):
+        return hash(self.hash)
+
+
+Kminmer = KminmerHash  # KminmerType, src/lib.rs:39
+
+
+def _as_u8(seq) -> np.ndarray:
+    if isinstance(seq, str):
+        seq = seq.encode()
+    if isinstance(seq, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(seq), dtype=np.uint8)
+    return np.ascontiguousarray(seq, dtype=np.uint8)
+
+
+class Context:
+    """One s2k_ctx: one CUDA device, one stream, grow-only buffers.  Single-threaded, like one iterator."""
+
+    def __init__(self, device: int = 0, lib: Optional[Library] = None):
+        self.lib = lib or default_library()
+        h = C.c_void_p()
+        st = self.lib.c.s2k_ctx_create(int(device), C.byref(h))
+        if st != 0:
+            raise S2KError(st, self.lib.c.s2k_strerror(st).decode() +
+                           " (s2k_ctx_create: is a CUDA device visible? this path has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.c.s2k_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st: int):
+        if st != 0:
+            msg = self.lib.c.s2k_last_error(self.h).decode() or self.lib.c.s2k_strerror(st).decode()
+            raise S2KError(st, msg)
+
+    # -- host buffers in, host (pinned) results out ------------------------------------------------------
+    def run(self, bases, seq_off, l: int, k: int, density: float, mode: HashMode,
+            variant: HashVariant = HashVariant.NT1_32, want_minimizers: bool = False, copy: bool = True) -> KminmersBatch:
+        b = _as_u8(bases)
+        so = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        if so.ndim != 1 or so.shape[0] < 1:
+            raise ValueError("seq_off must hold n_seqs+1 offsets")
+        n = so.shape[0] - 1
+        if int(so[-1]) > b.shape[0]:
+            raise ValueError("seq_off[-1] exceeds len(bases)")
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 1 if want_minimizers else 0))
+        p = _Params(int(l), int(k), float(density), int(mode), int(variant))
+        r = _Result()
+        self._check(self.lib.c.s2k_run(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(p), C.byref(r)))
+        f = (lambda a: a.copy()) if copy else (lambda a: a)
+        mins = f(_view(r.minimizers, r.n_minimizers, MINIMIZER_DTYPE)) if want_minimizers else None
+        return KminmersBatch(n, f(_view(r.hash, r.n_items, np.uint64)), f(_view(r.start, r.n_items, np.uint32)),
+                             f(_view(r.end, r.n_items, np.uint32)), f(_view(r.rev, r.n_items, np.uint8)),
+                             f(_view(r.km_off, n + 1, np.uint64)), f(_view(r.min_off, n + 1, np.uint64)),
+                             f(_view(r.min_cnt, n, np.uint32)), int(r.n_minimizers), mins)
+
+    # -- device buffers in, device results out ------------------------------------------------------------
+    def run_device(self, d_bases_ptr: int, d_seq_off_ptr: int, n_seqs: int, n_bases: int, l: int, k: int,
+                   density: float, mode: HashMode, variant: HashVariant = HashVariant.NT1_32, stream: int = 0) -> _Result:
+        """Raw device-pointer form (pointers as ints).  Returns the ctypes result struct (device pointers)."""
+        p = _Params(int(l), int(k), float(density), int(mode), int(variant))
+        r = _Result()
+        self._check(self.lib.c.s2k_run_device(self.h, C.c_void_p(d_bases_ptr), C.c_void_p(d_seq_off_ptr), int(n_seqs),
+                                              int(n_bases), C.byref(p), C.c_void_p(stream), C.byref(r)))
+        return r
+
+    def encode_rle(self, bases, seq_off):
+        b = _as_u8(bases)
+        so = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        n = so.shape[0] - 1
+        r = _RleResult()
+        self._check(self.lib.c.s2k_encode_rle(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(r)))
+        return (_view(r.hpc, r.n_hpc, np.uint8).copy(), _view(r.pos, r.n_hpc, np.uint32).copy(),
+                _view(r.hpc_off, n + 1, np.uint64).copy())
+
+    def set_timing(self, enabled: bool):
+        self._check(self.lib.c.s2k_ctx_set_timing(self.h, 1 if enabled else 0))
+
+    def last_kernel_ms(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_uint32()
+        self._check(self.lib.c.s2k_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.c.s2k_launch_count(self.h))
+
+
+_ctx: Optional[Context] = None
+
+
+def _default_ctx() -> Context:
+    global _ctx
+    if _ctx is None:
+        _ctx = Context(0)
+    return _ctx
+
+
+class KminmersIterator:
+    """KminmersIterator::new(seq, l, k, density, mode) (src/lib.rs:89) as a Python iterator of KminmerHash.
+
+    The whole sequence is processed on the GPU at construction (a batch of one); iteration then yields the
+    items in the reference's order.  For throughput use Context.run on many sequences at once."""
+
+    def __init__(self, seq, l: int, k: int, density: float, mode: HashMode,
+                 variant: HashVariant = HashVariant.NT1_32, ctx: Optional[Context] = None):
+        s = _as_u8(seq)
+        ctx = ctx or _default_ctx()
+        self.batch = ctx.run(s, np.array([0, s.shape[0]], dtype=np.uint64), l, k, density, mode, variant)
+        self._it = self.batch.items(0)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> KminmerHash:
+        return next(self._it)
+
+
+class _MinimizerIterator:
+    mode = HashMode.Regular
+
+    def __init__(self, seq, l: int, hash_bound_density: float, ctx: Optional[Context] = None,
+                 variant: HashVariant = HashVariant.NT1_32):
+        s = _as_u8(seq)
+        ctx = ctx or _default_ctx()
+        b = ctx.run(s, np.array([0, s.shape[0]], dtype=np.uint64), l, 1, hash_bound_density, self.mode, variant,
+                    want_minimizers=True)
+        self.items = b.minimizers_of(0)
+        self._i = 0
+
+    def __iter__(self):
+        return self
+
+
+class NtHashHPCIterator(_MinimizerIterator):
+    """src/nthash_hpc.rs:193: Item = (start, end, hash).  Takes the density (the bound is derived as lib.rs:91)."""
+    mode = HashMode.Hpc
+
+    def __next__(self):
+        if self._i >= len(self.items):
+            raise StopIteration
+        m = self.items[self._i]
+        self._i += 1
+        return int(m["start"]), int(m["end"]), int(m["hash"])
+
+
+class NtHashHPCSIMDIterator(NtHashHPCIterator):
+    """src/nthash_hpc_simd.rs:59: Item = (start, end, hash)."""
+    mode = HashMode.HpcSimd
+
+
+class NtHashSIMDIterator(_MinimizerIterator):
+    """src/nthash_avx512_32.rs:82: Item = (pos, hash)."""
+    mode = HashMode.Simd
+
+    def __next__(self):
+        if self._i >= len(self.items):
+            raise StopIteration
+        m = self.items[self._i]
+        self._i += 1
+        return int(m["start"]), int(m["hash"])
+
+
+def encode_rle_simd(seq, ctx: Optional[Context] = None):
+    """src/hpc.rs:44: (hpc bytes, run-start positions u32)."""
+    s = _as_u8(seq)
+    ctx = ctx or _default_ctx()
+    h, p, _ = ctx.encode_rle(s, np.array([0, s.shape[0]], dtype=np.uint64))
+    return h.tobytes(), p
+
+
+def encode_rle(seq, ctx: Optional[Context] = None):
+    """src/hpc.rs:7: same keep rule on ACGTN input; positions widened to u64 like Vec<usize>."""
+    h, p = encode_rle_simd(seq, ctx)
+    return h, p.astype(np.uint64)
+
+
+def hpc(seq, ctx: Optional[Context] = None) -> bytes:
+    """src/hpc.rs:28."""
+    return encode_rle_simd(seq, ctx)[0]

@@ -1,0 +1,645 @@
+// s2k_api.cu -- C ABI (include/seq2kminmers.h) over the sm_100a kernels in s2k_kernels.cuh.
+// Host side of the drop-in boundary: parameter validation mirroring the reference's panics, the exact
+// float recipe for the selection bounds, table construction, buffer management and launch sequencing.
+// There is no CPU fallback: every entry point that computes anything launches CUDA kernels or fails.
+#include "../../include/seq2kminmers.h"
+#include "s2k_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+using namespace s2k;
+
+// Kernel launch.  `conc` only matters to the test-tier host emulation (tests/emu): kernels with static shared
+// state run their blocks one after the other there.
+#ifdef S2K_EMU
+#define S2K_LAUNCH(kfn, grid, block, smem, stream, conc, ...) \
+    emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), conc, [&]() { kfn(__VA_ARGS__); })
+#else
+#define S2K_LAUNCH(kfn, grid, block, smem, stream, conc, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ bounds
+// src/lib.rs:91: ((density as f64) * (u32::MAX as f64)) as u32   (Rust `as` saturates, NaN -> 0)
+uint32_t bound_scalar(double density)
+{
+    const double v = density * 4294967295.0;
+    if (!(v > 0.0)) return 0u;
+    if (v >= 4294967295.0) return 0xffffffffu;
+    return (uint32_t)v;
+}
+// src/nthash_avx512_32.rs:47-48: density = bound/u32::MAX (f64); ((density as f32) * (u32::MAX as f32)) as u32
+uint32_t bound_simd(uint32_t b)
+{
+    const double dd = (double)b / 4294967295.0;
+    const float f = (float)dd;
+    volatile float prod = f * 4294967296.0f;
+    if (!(prod > 0.0f)) return 0u;
+    if (prod >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)prod;
+}
+
+const uint64_t SEED64[4] = {0x3c8bfbb395c60474ull, 0x3193c18562a02b4cull, 0x20323ed082572324ull,
+                            0x295549f54be24456ull};   // A C G T, src/nthash_hpc.rs:31-34
+
+uint32_t rolw(uint32_t x, unsigned r, int w)
+{
+    r %= (unsigned)w;
+    if (!r) return x;
+    const uint32_t m = w == 32 ? 0xffffffffu : 0x7fffffffu;
+    return ((x << r) | (x >> (w - r))) & m;
+}
+uint32_t rorw(uint32_t x, unsigned r, int w) { r %= (unsigned)w; return rolw(x, (unsigned)w - r, w); }
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool host = false;
+};
+
+struct Timing {
+    bool enabled = false;
+    cudaEvent_t ev[64][2];
+    int n = 0;           // minimizer-kernel launches recorded
+    cudaEvent_t wv[2];   // window-kernel
+    bool created = false;
+    double min_ms = 0, win_ms = 0;
+    uint32_t min_launches = 0;
+};
+
+} // namespace
+
+struct s2k_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t flags = 0;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    double rate_hint = 0.0;         // observed minimizers per base (grow-only)
+    // device buffers
+    Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_hpc_off, d_km_off, d_min_cnt;
+    Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos;
+    // pinned host result buffers
+    Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
+    Timing tm;
+    bool attr_set = false;
+};
+
+namespace {
+
+int fail(s2k_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? S2K_ERR_OOM : S2K_ERR_CUDA,          \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                        \
+    } while (0)
+
+int ensure(s2k_ctx *ctx, Buf &b, size_t bytes, bool host)
+{
+    if (bytes <= b.cap && b.p) return S2K_OK;
+    if (b.p) {
+        if (b.host) cudaFreeHost(b.p); else cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+    }
+    size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+    want = (want + 255) & ~size_t(255);
+    cudaError_t e = host ? cudaMallocHost(&b.p, want) : cudaMalloc(&b.p, want);
+    if (e != cudaSuccess && want > bytes) {          // retry without slack
+        (void)cudaGetLastError();
+        want = (std::max<size_t>(bytes, 256) + 255) & ~size_t(255);
+        e = host ? cudaMallocHost(&b.p, want) : cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        b.p = nullptr;
+        return fail(ctx, S2K_ERR_OOM, std::string("allocation of ") + std::to_string(want) + " bytes failed: " +
+                                          cudaGetErrorString(e));
+    }
+    b.cap = want; b.host = host;
+    return S2K_OK;
+}
+void release(Buf &b)
+{
+    if (b.p) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
+    b.p = nullptr; b.cap = 0;
+}
+
+struct Plan {
+    bool hpc, simd, w31, quirk;
+    uint32_t l, k, d, need, thr, halo, tile;
+    bool none;       // threshold selects nothing
+    uint8_t lut[256];
+    uint2 xy[64];
+};
+
+// Validation mirrors the reference's panics: assert!(k<=31) (src/nthash_avx512_32.rs:33) for the SIMD modes,
+// KSizeTooBig / assert!(k<256) (src/nthash_hpc.rs:123-133) for the scalar ones.
+int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
+{
+    if (!p) return fail(ctx, S2K_ERR_NULL, "params is null");
+    if (p->mode < S2K_MODE_REGULAR || p->mode > S2K_MODE_HPCSIMD) return fail(ctx, S2K_ERR_BAD_PARAM, "unknown hash mode");
+    if (p->variant != S2K_HASH_NT1_32 && p->variant != S2K_HASH_NT2_31) return fail(ctx, S2K_ERR_BAD_PARAM, "unknown hash variant");
+    if (p->l == 0 || p->k == 0) return fail(ctx, S2K_ERR_BAD_PARAM, "l and k must be >= 1");
+    P.hpc = p->mode == S2K_MODE_HPC || p->mode == S2K_MODE_HPCSIMD;
+    P.simd = p->mode == S2K_MODE_SIMD || p->mode == S2K_MODE_HPCSIMD;
+    P.w31 = p->variant == S2K_HASH_NT2_31;
+    if (P.w31 && !P.simd) return fail(ctx, S2K_ERR_BAD_PARAM, "the 31-bit variant replaces the SIMD iterator only (modes Simd/HpcSimd)");
+    if (P.simd && p->l > 31) return fail(ctx, S2K_ERR_L_TOO_BIG, "l must be <= 31 in the Simd/HpcSimd modes");
+    if (!P.simd && p->l >= 256) return fail(ctx, S2K_ERR_L_TOO_BIG, "l must be < 256 in the Regular/Hpc modes");
+    if (p->k > 0x7fffffffu) return fail(ctx, S2K_ERR_BAD_PARAM, "k too large");
+    P.l = p->l; P.k = p->k;
+    P.d = (p->mode == S2K_MODE_HPC) ? 1u : 0u;       // Hpc: the l-mer is emitted when the NEXT kept base shows up
+    P.need = P.l - 1 + P.d;
+    P.quirk = P.simd && !P.w31;
+    P.halo = P.need >= 128 ? 512u : 256u;
+    P.tile = (uint32_t)WIN - P.halo;
+    const uint32_t bs = bound_scalar(p->density);
+    uint64_t excl;                                   // select iff hash < excl
+    if (P.simd) { uint32_t b = bound_simd(bs); if (P.w31) b /= 2; excl = b; }
+    else excl = (uint64_t)bs + 1;
+    P.none = excl == 0;
+    P.thr = P.none ? 0u : (uint32_t)(excl - 1);
+    // base classes: 0..3 = A C G T, 4 = seed 0, 5 = seed 1
+    const int w = P.w31 ? 31 : 32;
+    uint32_t h[8] = {0}, rc[8] = {0};
+    for (int b = 0; b < 4; ++b) {
+        h[b] = P.w31 ? (uint32_t)(SEED64[b] >> 33) : (uint32_t)SEED64[b];
+        rc[b] = P.w31 ? (uint32_t)(SEED64[3 - b] >> 33) : (uint32_t)SEED64[3 - b];
+    }
+    h[5] = rc[5] = 1;
+    if (P.simd) {                                    // low nibble, src/nthash_avx512_32.rs:178-193
+        static const uint8_t nib[16] = {4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4};
+        for (int i = 0; i < 256; ++i) P.lut[i] = nib[i & 15];
+    } else {                                         // src/nthash_hpc.rs:29-49
+        for (int i = 0; i < 256; ++i) P.lut[i] = 5;
+        P.lut['A'] = 0; P.lut['C'] = 1; P.lut['G'] = 2; P.lut['T'] = 3; P.lut['N'] = 4;
+    }
+    for (int o = 0; o < 8; ++o)
+        for (int i = 0; i < 8; ++i) {
+            P.xy[o * 8 + i].x = rolw(h[o], P.l, w) ^ h[i];
+            P.xy[o * 8 + i].y = rorw(rc[o], 1, w) ^ rolw(rc[i], P.l - 1, w);
+        }
+    return S2K_OK;
+}
+
+template <typename T> T *ptr(Buf &b) { return reinterpret_cast<T *>(b.p); }
+
+constexpr uint64_t SLAB_TILES = 131072;              // tiles per minimizer launch (< 2^30 bases: 31-bit look-back fields)
+
+int set_attrs(s2k_ctx *ctx)
+{
+    if (ctx->attr_set) return S2K_OK;
+    const int smem = (int)sizeof(Smem);
+    CU(cudaFuncSetAttribute(k_minimizers<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_minimizers<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_minimizers<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_minimizers<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ctx->attr_set = true;
+    return S2K_OK;
+}
+
+void timing_prepare(s2k_ctx *ctx)
+{
+    Timing &T = ctx->tm;
+    if (T.enabled && !T.created) {
+        for (auto &e : T.ev) { cudaEventCreate(&e[0]); cudaEventCreate(&e[1]); }
+        cudaEventCreate(&T.wv[0]); cudaEventCreate(&T.wv[1]);
+        T.created = true;
+    }
+    T.n = 0;
+}
+
+// d_small layout (uint64 words): [0..1] carry A, [2..3] carry B, [4] ticket(u32), [5] err(u32), [6] ticket2(u32)
+// Runs the whole device pipeline on `st`.  On return the totals have been read back (one sync).
+int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs, uint64_t n_bases,
+               const Plan &P, cudaStream_t st, s2k_result *out)
+{
+    int rc;
+    if ((rc = set_attrs(ctx)) != S2K_OK) return rc;
+    timing_prepare(ctx);
+    std::memset(out, 0, sizeof(*out));
+    out->n_seqs = n_seqs;
+    out->location = S2K_LOC_DEVICE;
+
+    if ((rc = ensure(ctx, ctx->d_small, 64, false))) return rc;
+    if ((rc = ensure(ctx, ctx->h_small, 64, true))) return rc;
+    if ((rc = ensure(ctx, ctx->d_min_off, (n_seqs + 1) * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_km_off, (n_seqs + 1) * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_min_cnt, std::max<uint64_t>(n_seqs, 1) * 4, false))) return rc;
+    const bool want_hpc_off = P.hpc && P.quirk;
+    if (want_hpc_off && (rc = ensure(ctx, ctx->d_hpc_off, (n_seqs + 1) * 8, false))) return rc;
+
+    uint64_t *small = ptr<uint64_t>(ctx->d_small);
+    uint64_t *hsmall = ptr<uint64_t>(ctx->h_small);
+    uint64_t n_min = 0;
+
+    if (n_bases == 0 || n_seqs == 0 || P.none) {
+        CU(cudaMemsetAsync(ctx->d_min_off.p, 0, (n_seqs + 1) * 8, st));
+        CU(cudaMemsetAsync(ctx->d_km_off.p, 0, (n_seqs + 1) * 8, st));
+        CU(cudaMemsetAsync(ctx->d_min_cnt.p, 0, std::max<uint64_t>(n_seqs, 1) * 4, st));
+        CU(cudaStreamSynchronize(st));
+        out->km_off = ptr<uint64_t>(ctx->d_km_off);
+        out->min_off = ptr<uint64_t>(ctx->d_min_off);
+        out->min_cnt = ptr<uint32_t>(ctx->d_min_cnt);
+        return S2K_OK;
+    }
+
+    const uint64_t slab_len = SLAB_TILES * (uint64_t)P.tile;
+    const uint64_t n_slabs = (n_bases + slab_len - 1) / slab_len;
+    const uint64_t max_tiles = std::min<uint64_t>(SLAB_TILES, (n_bases + P.tile - 1) / P.tile);
+    if ((rc = ensure(ctx, ctx->d_tile_lb, (max_tiles + 1) * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_status, std::max<uint64_t>(max_tiles, (n_seqs + RT * RPT - 1) / (RT * RPT)) * 8 + 8, false))) return rc;
+
+    // capacity of the minimizer stream: expected 2*density*(kept bases), with head room; grown and rerun on overflow
+    uint64_t cap;
+    {
+        const double frac = std::min(1.0, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+        double rate = std::min(1.0, 2.0 * frac) * 1.15 + 0.0005;
+        rate = std::max(rate, ctx->rate_hint * 1.05);
+        cap = std::min<uint64_t>(n_bases, (uint64_t)((double)n_bases * rate) + 65536);
+    }
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = ensure(ctx, ctx->d_mins, cap * sizeof(uint4), false))) return rc;
+        CU(cudaMemsetAsync(small, 0, 64, st));
+        for (uint64_t s = 0; s < n_slabs; ++s) {
+            K1Args A;
+            A.bases = d_bases; A.seq_off = d_seq_off;
+            A.tile_lb = ptr<uint32_t>(ctx->d_tile_lb);
+            A.status = ptr<uint64_t>(ctx->d_status);
+            A.ticket = reinterpret_cast<uint32_t *>(small + 4);
+            A.carry_in = small + ((s & 1) ? 2 : 0);
+            A.carry_out = small + ((s & 1) ? 0 : 2);
+            A.min_out = ptr<uint4>(ctx->d_mins); A.min_cap = cap;
+            A.min_off = ptr<uint64_t>(ctx->d_min_off);
+            A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+            A.err = reinterpret_cast<uint32_t *>(small + 5);
+            A.n_seqs = n_seqs; A.n_bases = n_bases;
+            A.slab_begin = s * slab_len; A.slab_end = std::min(n_bases, (s + 1) * slab_len);
+            A.n_tiles = (uint32_t)((A.slab_end - A.slab_begin + P.tile - 1) / P.tile);
+            A.tile = P.tile; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
+            std::memcpy(A.cls_lut, P.lut, 256);
+            std::memcpy(A.xy, P.xy, sizeof(P.xy));
+
+            CU(cudaMemsetAsync(A.status, 0, (uint64_t)A.n_tiles * 8, st));
+            CU(cudaMemsetAsync(A.ticket, 0, 4, st));
+            S2K_LAUNCH(k_tile_bounds, (A.n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, A.slab_begin,
+                       A.slab_end, P.tile, A.n_tiles, ptr<uint32_t>(ctx->d_tile_lb));
+            const int grid = (int)std::min<uint64_t>(A.n_tiles, (uint64_t)ctx->sm_count * 3);
+            const size_t smem = sizeof(Smem);
+            Timing &T = ctx->tm;
+            const bool rec = T.enabled && T.n < 64;
+            if (rec) cudaEventRecord(T.ev[T.n][0], st);
+            void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
+                                              : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
+            S2K_LAUNCH(kfn, grid, NT, smem, st, true, A);
+            if (rec) { cudaEventRecord(T.ev[T.n][1], st); ++T.n; }
+            ctx->launches += 2;
+            CU(cudaGetLastError());
+        }
+        // totals -> host
+        const uint64_t *carry_final = small + ((n_slabs & 1) ? 2 : 0);
+        CU(cudaMemcpyAsync(hsmall, carry_final, 16, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        n_min = hsmall[0];
+        const uint32_t err = (uint32_t)hsmall[2];
+        if (err & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "tile look-back timed out");
+        if (n_min <= cap) break;
+        if (attempt == 1) return fail(ctx, S2K_ERR_INTERNAL, "minimizer capacity overflow after regrow");
+        cap = n_min;                                   // exact size known now: rerun once
+    }
+    ctx->rate_hint = std::max(ctx->rate_hint, (double)n_min / (double)n_bases);
+
+    // window stage
+    const uint64_t item_cap = std::max<uint64_t>(n_min, 1);
+    if ((rc = ensure(ctx, ctx->d_hash, item_cap * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_start, item_cap * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_end, item_cap * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rev, item_cap, false))) return rc;
+    {
+        K2Args B;
+        B.mins = ptr<uint4>(ctx->d_mins);
+        B.min_off = ptr<uint64_t>(ctx->d_min_off);
+        B.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+        B.seq_off = d_seq_off; B.bases = d_bases; B.n_seqs = n_seqs;
+        B.l = P.l; B.k = P.k; B.quirk = P.quirk; B.hpc = P.hpc;
+        B.km_off = ptr<uint64_t>(ctx->d_km_off);
+        B.min_cnt = ptr<uint32_t>(ctx->d_min_cnt);
+        B.status = ptr<uint64_t>(ctx->d_status);
+        B.ticket = reinterpret_cast<uint32_t *>(small + 6);
+        B.err = reinterpret_cast<uint32_t *>(small + 5);
+        const uint64_t rtiles = (n_seqs + RT * RPT - 1) / (RT * RPT);
+        CU(cudaMemsetAsync(B.status, 0, rtiles * 8, st));
+        CU(cudaMemsetAsync(B.ticket, 0, 4, st));
+        Timing &T = ctx->tm;
+        if (T.enabled) cudaEventRecord(T.wv[0], st);
+        const int grid = (int)std::min<uint64_t>(rtiles, (uint64_t)ctx->sm_count * 8);
+        S2K_LAUNCH(k_read_counts, grid, RT, 0, st, false, B);
+        CU(cudaGetLastError());
+        K3Args C;
+        C.mins = B.mins; C.min_off = B.min_off; C.km_off = B.km_off; C.n_min = n_min; C.k = P.k;
+        C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);
+        C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
+        if (n_min > 0) {
+            const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 16);
+            S2K_LAUNCH(k_windows, g3, 256, 0, st, false, C);
+            CU(cudaGetLastError());
+            ctx->launches += 1;
+        }
+        if (T.enabled) cudaEventRecord(T.wv[1], st);
+        ctx->launches += 1;
+        CU(cudaMemcpyAsync(hsmall + 4, B.km_off + n_seqs, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if ((uint32_t)hsmall[2] & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "scan look-back timed out");
+    }
+    if (ctx->tm.enabled) {
+        Timing &T = ctx->tm;
+        double ms = 0;
+        for (int i = 0; i < T.n; ++i) { float f = 0; cudaEventElapsedTime(&f, T.ev[i][0], T.ev[i][1]); ms += f; }
+        float f = 0; cudaEventElapsedTime(&f, T.wv[0], T.wv[1]);
+        T.min_ms = ms; T.win_ms = f; T.min_launches = (uint32_t)T.n;
+    }
+    out->n_minimizers = n_min;
+    out->n_items = hsmall[4];
+    out->hash = ptr<uint64_t>(ctx->d_hash);
+    out->start = ptr<uint32_t>(ctx->d_start);
+    out->end = ptr<uint32_t>(ctx->d_end);
+    out->rev = ptr<uint8_t>(ctx->d_rev);
+    out->km_off = ptr<uint64_t>(ctx->d_km_off);
+    out->minimizers = reinterpret_cast<const s2k_minimizer *>(ctx->d_mins.p);
+    out->min_off = ptr<uint64_t>(ctx->d_min_off);
+    out->min_cnt = ptr<uint32_t>(ctx->d_min_cnt);
+    return S2K_OK;
+}
+
+int check_offsets(s2k_ctx *ctx, const uint64_t *seq_off, uint64_t n_seqs)
+{
+    if (n_seqs >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_OFFSETS, "too many sequences in one batch (limit 2^32-16)");
+    if (seq_off[0] != 0) return fail(ctx, S2K_ERR_BAD_OFFSETS, "seq_off[0] must be 0");
+    for (uint64_t i = 0; i < n_seqs; ++i) {
+        if (seq_off[i + 1] < seq_off[i]) return fail(ctx, S2K_ERR_BAD_OFFSETS, "seq_off must be non-decreasing");
+        if (seq_off[i + 1] - seq_off[i] >= 0xffffffffull) return fail(ctx, S2K_ERR_BAD_OFFSETS, "a sequence has >= 2^32-1 bases");
+    }
+    return S2K_OK;
+}
+
+} // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int s2k_abi_version(void) { return S2K_ABI_VERSION; }
+
+const char *s2k_strerror(int status)
+{
+    switch (status) {
+    case S2K_OK: return "ok";
+    case S2K_ERR_BAD_PARAM: return "bad parameter";
+    case S2K_ERR_L_TOO_BIG: return "l out of range for the selected hash mode";
+    case S2K_ERR_CUDA: return "CUDA error";
+    case S2K_ERR_OOM: return "out of memory";
+    case S2K_ERR_BAD_OFFSETS: return "invalid sequence offsets";
+    case S2K_ERR_INTERNAL: return "internal device-side check failed";
+    case S2K_ERR_NULL: return "null pointer";
+    default: return "unknown status";
+    }
+}
+
+const char *s2k_last_error(const s2k_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void s2k_bounds(double density, uint32_t *b_scalar, uint32_t *b_simd, uint32_t *b_31)
+{
+    const uint32_t bs = bound_scalar(density), bv = bound_simd(bs);
+    if (b_scalar) *b_scalar = bs;
+    if (b_simd) *b_simd = bv;
+    if (b_31) *b_31 = bv / 2;
+}
+
+int s2k_ctx_create(int device, s2k_ctx **out)
+{
+    if (!out) return S2K_ERR_NULL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { (void)cudaGetLastError(); return S2K_ERR_CUDA; }
+    if (device < 0 || device >= count) return S2K_ERR_BAD_PARAM;
+    s2k_ctx *ctx = new (std::nothrow) s2k_ctx();
+    if (!ctx) return S2K_ERR_OOM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete ctx;
+        return S2K_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return S2K_OK;
+}
+
+void s2k_ctx_destroy(s2k_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+    Buf *all[] = {&ctx->d_bases, &ctx->d_seq_off, &ctx->d_tile_lb, &ctx->d_status, &ctx->d_small, &ctx->d_mins,
+                  &ctx->d_min_off, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
+                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
+                  &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
+                  &ctx->h_rle_hpc, &ctx->h_rle_pos};
+    for (Buf *b : all) release(*b);
+    if (ctx->tm.created) {
+        for (auto &e : ctx->tm.ev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
+        cudaEventDestroy(ctx->tm.wv[0]); cudaEventDestroy(ctx->tm.wv[1]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int s2k_ctx_set_flags(s2k_ctx *ctx, uint32_t flags)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    ctx->flags = flags;
+    return S2K_OK;
+}
+
+int s2k_ctx_set_timing(s2k_ctx *ctx, int enabled)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    ctx->tm.enabled = enabled != 0;
+    return S2K_OK;
+}
+
+int s2k_last_kernel_ms(const s2k_ctx *ctx, double *minimizer_ms, double *window_ms, uint32_t *minimizer_launches)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (minimizer_ms) *minimizer_ms = ctx->tm.min_ms;
+    if (window_ms) *window_ms = ctx->tm.win_ms;
+    if (minimizer_launches) *minimizer_launches = ctx->tm.min_launches;
+    return S2K_OK;
+}
+
+uint64_t s2k_launch_count(const s2k_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int s2k_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return S2K_ERR_NULL;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return S2K_ERR_OOM; }
+    return S2K_OK;
+}
+void s2k_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int s2k_run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs, uint64_t n_bases,
+                   const s2k_params *params, void *stream, s2k_result *out)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (!out || (!d_seq_off)) return fail(ctx, S2K_ERR_NULL, "null argument");
+    if (n_bases && !d_bases) return fail(ctx, S2K_ERR_NULL, "bases is null");
+    if (n_seqs >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_OFFSETS, "too many sequences in one batch");
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) != 0) return fail(ctx, S2K_ERR_BAD_PARAM, "device bases must be 16-byte aligned");
+    Plan P;
+    int rc = make_plan(ctx, params, P);
+    if (rc != S2K_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    ctx->err.clear();
+    return run_device(ctx, d_bases, d_seq_off, n_seqs, n_bases, P, st, out);
+}
+
+int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const s2k_params *params,
+            s2k_result *out)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (!out || !seq_off) return fail(ctx, S2K_ERR_NULL, "null argument");
+    Plan P;
+    int rc = make_plan(ctx, params, P);
+    if (rc != S2K_OK) return rc;
+    if ((rc = check_offsets(ctx, seq_off, n_seqs)) != S2K_OK) return rc;
+    const uint64_t n_bases = seq_off[n_seqs];
+    if (n_bases && !bases) return fail(ctx, S2K_ERR_NULL, "bases is null");
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    cudaStream_t st = ctx->stream;
+    if ((rc = ensure(ctx, ctx->d_bases, n_bases + 16, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_seq_off, (n_seqs + 1) * 8, false))) return rc;
+    if (n_bases) CU(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_seq_off.p, seq_off, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    s2k_result dev;
+    rc = run_device(ctx, ptr<uint8_t>(ctx->d_bases), ptr<uint64_t>(ctx->d_seq_off), n_seqs, n_bases, P, st, &dev);
+    if (rc != S2K_OK) return rc;
+    const uint64_t ni = dev.n_items, nm = dev.n_minimizers;
+    if ((rc = ensure(ctx, ctx->h_hash, std::max<uint64_t>(ni, 1) * 8, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_start, std::max<uint64_t>(ni, 1) * 4, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_end, std::max<uint64_t>(ni, 1) * 4, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_rev, std::max<uint64_t>(ni, 1), true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_km_off, (n_seqs + 1) * 8, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_min_off, (n_seqs + 1) * 8, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_min_cnt, std::max<uint64_t>(n_seqs, 1) * 4, true))) return rc;
+    if (ni) {
+        CU(cudaMemcpyAsync(ctx->h_hash.p, dev.hash, ni * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_start.p, dev.start, ni * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_end.p, dev.end, ni * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_rev.p, dev.rev, ni, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(ctx->h_km_off.p, dev.km_off, (n_seqs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_min_off.p, dev.min_off, (n_seqs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (n_seqs) CU(cudaMemcpyAsync(ctx->h_min_cnt.p, dev.min_cnt, n_seqs * 4, cudaMemcpyDeviceToHost, st));
+    const bool want_min = (ctx->flags & S2K_WANT_MINIMIZERS) != 0;
+    if (want_min) {
+        if ((rc = ensure(ctx, ctx->h_mins, std::max<uint64_t>(nm, 1) * 16, true))) return rc;
+        if (nm) CU(cudaMemcpyAsync(ctx->h_mins.p, dev.minimizers, nm * 16, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    *out = dev;
+    out->location = S2K_LOC_HOST;
+    out->hash = ptr<uint64_t>(ctx->h_hash);
+    out->start = ptr<uint32_t>(ctx->h_start);
+    out->end = ptr<uint32_t>(ctx->h_end);
+    out->rev = ptr<uint8_t>(ctx->h_rev);
+    out->km_off = ptr<uint64_t>(ctx->h_km_off);
+    out->min_off = ptr<uint64_t>(ctx->h_min_off);
+    out->min_cnt = ptr<uint32_t>(ctx->h_min_cnt);
+    out->minimizers = want_min ? reinterpret_cast<const s2k_minimizer *>(ctx->h_mins.p) : nullptr;
+    return S2K_OK;
+}
+
+int s2k_encode_rle(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, s2k_rle_result *out)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (!out || !seq_off) return fail(ctx, S2K_ERR_NULL, "null argument");
+    int rc;
+    if ((rc = check_offsets(ctx, seq_off, n_seqs)) != S2K_OK) return rc;
+    const uint64_t n_bases = seq_off[n_seqs];
+    if (n_bases && !bases) return fail(ctx, S2K_ERR_NULL, "bases is null");
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    cudaStream_t st = ctx->stream;
+    std::memset(out, 0, sizeof(*out));
+    out->n_seqs = n_seqs; out->location = S2K_LOC_HOST;
+    if ((rc = ensure(ctx, ctx->h_min_off, (n_seqs + 1) * 8, true))) return rc;
+    if (n_bases == 0) {
+        std::memset(ctx->h_min_off.p, 0, (n_seqs + 1) * 8);
+        out->hpc_off = ptr<uint64_t>(ctx->h_min_off);
+        return S2K_OK;
+    }
+    const uint64_t n_tiles64 = (n_bases + RLE_TILE - 1) / RLE_TILE;
+    if (n_tiles64 > 0x7fffffffull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large for s2k_encode_rle");
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+    if ((rc = ensure(ctx, ctx->d_bases, n_bases + 16, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_seq_off, (n_seqs + 1) * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_small, 64, false))) return rc;
+    if ((rc = ensure(ctx, ctx->h_small, 64, true))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_status, (uint64_t)n_tiles * 8 + 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rle_hpc, n_bases, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rle_pos, n_bases * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_hpc_off, (n_seqs + 1) * 8, false))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_seq_off.p, seq_off, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint64_t *small = ptr<uint64_t>(ctx->d_small);
+    CU(cudaMemsetAsync(small, 0, 64, st));
+    CU(cudaMemsetAsync(ctx->d_status.p, 0, (uint64_t)n_tiles * 8, st));
+    S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, ptr<uint64_t>(ctx->d_seq_off), n_seqs,
+               (uint64_t)0, n_bases, (uint32_t)RLE_TILE, n_tiles, ptr<uint32_t>(ctx->d_tile_lb));
+    K4Args A;
+    A.bases = ptr<uint8_t>(ctx->d_bases); A.seq_off = ptr<uint64_t>(ctx->d_seq_off);
+    A.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
+    A.status = ptr<uint64_t>(ctx->d_status); A.ticket = reinterpret_cast<uint32_t *>(small + 4);
+    A.err = reinterpret_cast<uint32_t *>(small + 5);
+    A.hpc = ptr<uint8_t>(ctx->d_rle_hpc); A.pos = ptr<uint32_t>(ctx->d_rle_pos); A.hpc_off = ptr<uint64_t>(ctx->d_hpc_off);
+    S2K_LAUNCH(k_rle, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 8), NT, 0, st, false, A);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(ctx->h_min_off.p, ctx->d_hpc_off.p, (n_seqs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_small.p, small + 5, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((uint32_t)ptr<uint64_t>(ctx->h_small)[0] & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "tile look-back timed out");
+    const uint64_t n_hpc = ptr<uint64_t>(ctx->h_min_off)[n_seqs];
+    if ((rc = ensure(ctx, ctx->h_rle_hpc, std::max<uint64_t>(n_hpc, 1), true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_rle_pos, std::max<uint64_t>(n_hpc, 1) * 4, true))) return rc;
+    CU(cudaMemcpyAsync(ctx->h_rle_hpc.p, ctx->d_rle_hpc.p, n_hpc, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_rle_pos.p, ctx->d_rle_pos.p, n_hpc * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out->n_hpc = n_hpc;
+    out->hpc = ptr<uint8_t>(ctx->h_rle_hpc);
+    out->pos = ptr<uint32_t>(ctx->h_rle_pos);
+    out->hpc_off = ptr<uint64_t>(ctx->h_min_off);
+    return S2K_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,175 @@
+// cuda_emu.h -- TEST-ONLY shim that lets the product's CUDA sources (s2k_kernels.cuh, s2k_api.cu) be
+// compiled by g++ and executed on host threads, one std::thread per CUDA thread, with real barriers for
+// __syncthreads and lock-step warp collectives.  It exists so that the kernel LOGIC (tile stitching, halos,
+// look-back, tail rules, edge cases) can be checked against the oracle in the CPU-only test tier, where no
+// GPU is available.  It is never part of the product: rust-seq2kminmers_b200 loads libs2k_b200.so (nvcc,
+// sm_100a) and nothing else; this header is only ever included when tests/emu/build_emu.sh defines S2K_EMU.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <sched.h>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __restrict__
+#define __align__(n) alignas(n)
+
+struct uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+
+namespace emu {
+struct Block {
+    std::unique_ptr<std::barrier<>> bar;
+    std::vector<std::unique_ptr<std::barrier<>>> wbar;
+    std::vector<uint64_t> slot;      // 32 per warp
+    uint8_t *smem = nullptr;
+};
+inline thread_local Block *blk = nullptr;
+inline thread_local emu_dim3 tIdx, bIdx, bDim, gDim;
+
+// Runs `body` once per emulated CUDA thread.  concurrent=false runs the blocks one after the other (needed for
+// kernels that keep static __shared__ state, which the shim maps to plain statics).
+inline void launch(unsigned grid, unsigned block, size_t smem_bytes, bool concurrent, const std::function<void()> &body)
+{
+    auto run_block = [&](unsigned b, std::vector<std::thread> &threads, Block &B) {
+        B.bar = std::make_unique<std::barrier<>>(block);
+        const unsigned nw = (block + 31) / 32;
+        for (unsigned w = 0; w < nw; ++w) B.wbar.push_back(std::make_unique<std::barrier<>>(std::min(32u, block - 32 * w)));
+        B.slot.assign((size_t)nw * 32, 0);
+        B.smem = smem_bytes ? (uint8_t *)aligned_alloc(128, (smem_bytes + 127) & ~size_t(127)) : nullptr;
+        for (unsigned t = 0; t < block; ++t)
+            threads.emplace_back([&, b, t]() {
+                blk = &B; tIdx.x = t; bIdx.x = b; bDim.x = block; gDim.x = grid;
+                body();
+            });
+    };
+    if (concurrent) {
+        std::vector<Block> blocks(grid);
+        std::vector<std::thread> threads;
+        threads.reserve((size_t)grid * block);
+        for (unsigned b = 0; b < grid; ++b) run_block(b, threads, blocks[b]);
+        for (auto &t : threads) t.join();
+        for (auto &B : blocks) free(B.smem);
+    } else {
+        for (unsigned b = 0; b < grid; ++b) {
+            Block B;
+            std::vector<std::thread> threads;
+            threads.reserve(block);
+            run_block(b, threads, B);
+            for (auto &t : threads) t.join();
+            free(B.smem);
+        }
+    }
+}
+} // namespace emu
+
+#define threadIdx emu::tIdx
+#define blockIdx emu::bIdx
+#define blockDim emu::bDim
+#define gridDim emu::gDim
+
+static inline void __syncthreads() { emu::blk->bar->arrive_and_wait(); }
+
+template <typename T> static inline T emu_warp_exchange(T v, int src_lane_or_neg, bool take)
+{
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    emu::blk->slot[w * 32 + lane] = bits;
+    emu::blk->wbar[w]->arrive_and_wait();
+    T r = v;
+    if (take && src_lane_or_neg >= 0 && src_lane_or_neg < 32) {
+        uint64_t o = emu::blk->slot[w * 32 + (unsigned)src_lane_or_neg];
+        std::memcpy(&r, &o, sizeof(T));
+    }
+    emu::blk->wbar[w]->arrive_and_wait();
+    return r;
+}
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int o)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    return emu_warp_exchange(v, lane - o, lane >= o);
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int o)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    return emu_warp_exchange(v, lane ^ o, true);
+}
+static inline unsigned __ballot_sync(unsigned, bool pred)
+{
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    emu::blk->slot[w * 32 + lane] = pred ? 1 : 0;
+    emu::blk->wbar[w]->arrive_and_wait();
+    unsigned r = 0;
+    const unsigned n = std::min(32u, blockDim.x - 32 * w);
+    for (unsigned i = 0; i < n; ++i) r |= (unsigned)emu::blk->slot[w * 32 + i] << i;
+    emu::blk->wbar[w]->arrive_and_wait();
+    return r;
+}
+
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline unsigned __vcmpne4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) if (((a >> (8 * i)) & 0xff) != ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i);
+    return r;
+}
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s)
+{
+    s &= 31;
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s)
+{
+    s &= 31;
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+static inline void __nanosleep(unsigned) { sched_yield(); }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
+
+// ------------------------------------------------------------------------------------------------ runtime API
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaDevAttrMultiProcessorCount = 16, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~size_t(255)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)1; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { const char *e = getenv("S2K_EMU_SMS"); *v = e ? atoi(e) : 1; return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
