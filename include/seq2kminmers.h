@@ -143,6 +143,11 @@ typedef struct s2k_rle_result {
 int s2k_encode_rle(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs,
                    s2k_rle_result *out);
 
+/* Synthetic workload of SURVEY.md 8(d), written straight into device memory: bases [first, first+count) of the
+ * stream base(i) = "ACGT"[(splitmix64(seed, i>>5) >> 2*(i&31)) & 3].  Benchmark/test utility, not part of the
+ * reference's API.  With stream == NULL the call runs on the context's stream and waits for it. */
+int s2k_synth_device(s2k_ctx *ctx, uint64_t seed, uint64_t first, uint64_t count, uint8_t *d_out, void *stream);
+
 /* Selection bounds exactly as the reference derives them (src/lib.rs:91, src/nthash_avx512_32.rs:47-48,
  * src/nthash2_avx512_32.rs:52-54). */
 void s2k_bounds(double density, uint32_t *bound_scalar, uint32_t *bound_simd, uint32_t *bound_31);

@@ -80,7 +80,7 @@ MINIMIZER_DTYPE = np.dtype([("hash", "<u4"), ("start", "<u4"), ("end", "<u4"), (
 ABI_SYMBOLS = (
     "s2k_ctx_create", "s2k_ctx_destroy", "s2k_ctx_set_flags", "s2k_run", "s2k_run_device", "s2k_encode_rle",
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
-    "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms",
+    "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
 )
 
 
@@ -123,6 +123,8 @@ class Library:
         L.s2k_launch_count.argtypes = [vp]
         L.s2k_ctx_set_timing.restype = C.c_int
         L.s2k_ctx_set_timing.argtypes = [vp, C.c_int]
+        L.s2k_synth_device.restype = C.c_int
+        L.s2k_synth_device.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
         L.s2k_last_kernel_ms.restype = C.c_int
         L.s2k_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
 
@@ -283,6 +285,11 @@ class Context:
                                               int(n_bases), C.byref(p), C.c_void_p(stream), C.byref(r)))
         return r
 
+    def synth_device(self, seed: int, first: int, count: int, d_out_ptr: int, stream: int = 0):
+        """Fill device memory with the synthetic base stream of SURVEY.md 8(d)."""
+        self._check(self.lib.c.s2k_synth_device(self.h, int(seed), int(first), int(count), C.c_void_p(d_out_ptr),
+                                                C.c_void_p(stream)))
+
     def encode_rle(self, bases, seq_off):
         b = _as_u8(bases)
         so = np.ascontiguousarray(seq_off, dtype=np.uint64)
@@ -303,6 +310,15 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.c.s2k_launch_count(self.h))
+
+
+class DeviceArray:
+    """Zero-copy view of context-owned device memory (``__cuda_array_interface__``), e.g. for
+    ``torch.as_tensor(DeviceArray(ptr, n, "<u8"), device="cuda")``.  Valid until the next run on the context."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr or 0), False),
+                                         "version": 2, "strides": None}
 
 
 _ctx: Optional[Context] = None

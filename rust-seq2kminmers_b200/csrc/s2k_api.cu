@@ -504,6 +504,21 @@ int s2k_host_alloc(size_t bytes, void **out)
 }
 void s2k_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+int s2k_synth_device(s2k_ctx *ctx, uint64_t seed, uint64_t first, uint64_t count, uint8_t *d_out, void *stream)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (count && !d_out) return fail(ctx, S2K_ERR_NULL, "d_out is null");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    if (count) {
+        const int grid = (int)std::min<uint64_t>((count / 16 + 255) / 256 + 1, (uint64_t)ctx->sm_count * 16);
+        S2K_LAUNCH(k_synth, grid, 256, 0, st, false, seed, first, count, d_out);
+        CU(cudaGetLastError());
+    }
+    if (!stream) CU(cudaStreamSynchronize(st));
+    return S2K_OK;
+}
+
 int s2k_run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs, uint64_t n_bases,
                    const s2k_params *params, void *stream, s2k_result *out)
 {

@@ -763,4 +763,38 @@ __global__ void __launch_bounds__(NT) k_rle(const __grid_constant__ K4Args A)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ synthetic reads
+// Workload generator of SURVEY.md 8(d): 32 bases per 64-bit word, word(j) = splitmix64 finalizer of
+// seed + (j+1)*0x9E3779B97F4A7C15, base(i) = "ACGT"[(word(i>>5) >> 2*(i&31)) & 3].  Same data on host
+// (oracle/s2k_oracle.c: s2k_oracle_synth) and device without a transfer.
+__device__ __forceinline__ uint64_t synth_word(uint64_t seed, uint64_t j)
+{
+    uint64_t z = seed + (j + 1) * 0x9E3779B97F4A7C15ull;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+__global__ void __launch_bounds__(256) k_synth(uint64_t seed, uint64_t first, uint64_t count, uint8_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nvec = (count + 15) / 16;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint64_t t0 = v * 16;
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint64_t cur_j = ~0ull, word = 0;
+        for (int b = 0; b < 16; ++b) {
+            const uint64_t i = first + t0 + b;
+            if ((i >> 5) != cur_j) { cur_j = i >> 5; word = synth_word(seed, cur_j); }
+            const uint32_t c = (uint32_t)(word >> (2 * (i & 31))) & 3u;
+            w[b >> 2] |= ((0x54474341u >> (8 * c)) & 0xffu) << (8 * (b & 3));   // "ACGT"
+        }
+        if (t0 + 16 <= count && ((reinterpret_cast<uintptr_t>(out) + t0) & 15u) == 0) {
+            *reinterpret_cast<uint4 *>(out + t0) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int b = 0; b < 16 && t0 + b < count; ++b) out[t0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
 } // namespace s2k

@@ -1,0 +1,60 @@
+"""Parity cases shared by the emulation tier (CPU, tests/emu) and the GPU tier (C ABI on a B200).
+Each case: (label, bases, seq_off, [(l, k, density, mode, variant), ...])."""
+import numpy as np
+
+REG, HPC, SIMD, HPCSIMD = 0, 1, 2, 3
+
+
+def all_modes(l, k, d, nt2=True):
+    out = [(l, k, d, m, 0) for m in (REG, HPC, SIMD, HPCSIMD) if m in (REG, HPC) or l <= 31]
+    if nt2 and l <= 31:
+        out += [(l, k, d, SIMD, 1), (l, k, d, HPCSIMD, 1)]
+    return out
+
+
+def cases(B, fixture_seq, scale=1):
+    """B: conftest.Batches.  scale=1 for the CPU emulation tier, larger on the GPU."""
+    rng = B.rng
+    out = []
+    so1 = np.array([0, len(fixture_seq)], dtype=np.uint64)
+    # reference fixture: config 1 and the sweep of tests/main.rs:82-89
+    par = all_modes(31, 5, 0.01) + [(10, 5, 0.0001, REG, 0)]
+    sweep_l = (5, 7, 11, 17, 25, 31) if scale > 1 else (5, 17)
+    for l in sweep_l:
+        for k in ((2, 5, 8) if scale > 1 else (2, 8)):
+            par += [(l, k, 0.01, m, 0) for m in (REG, HPC, SIMD, HPCSIMD)]
+    out.append(("fixture", fixture_seq, so1, par))
+    # lengths 0..l+1 and friends, empty reads between, first/last empty
+    lens = [0, 0] + list(rng.integers(0, 80, 300 * scale)) + [0, 0, 0, 31, 32, 33, 30, 1, 2, 47, 48, 0]
+    b, so = B.batch(lens)
+    out.append(("short+empty", b, so, all_modes(31, 5, 0.05) + all_modes(5, 2, 0.3) + all_modes(17, 3, 0.1, nt2=False)))
+    # 150-bp reads (config 3 shape)
+    b, so = B.batch([150] * (300 * scale))
+    out.append(("150bp", b, so, all_modes(31, 5, 0.01) + all_modes(31, 2, 0.05, nt2=False)))
+    # homopolymers far longer than the halo, runs crossing tile boundaries, N blocks
+    parts = [B.seq(5000), np.full(20000, ord("A"), np.uint8), B.seq(3000), np.full(9000, ord("N"), np.uint8), B.seq(40),
+             np.full(300, ord("T"), np.uint8), B.seq(12000, runp=0.7)]
+    s1 = np.concatenate(parts)
+    b, so = B.pack([s1, B.seq(100), s1[::-1].copy(), np.full(8000, ord("C"), np.uint8), B.seq(500)])
+    out.append(("homopolymers", b, so, all_modes(31, 5, 0.05) + all_modes(7, 2, 0.2, nt2=False)))
+    # non-ACGT bytes: N, lower case, IUPAC, junk (scalar table vs nibble table)
+    b, so = B.batch([3000, 5000, 100, 20000], alphabet=b"ACGTNacgtnXRY-")
+    out.append(("non-ACGT", b, so, all_modes(21, 4, 0.1)))
+    # large l (scalar profiles only), incl. halo 512 path
+    b, so = B.batch([30000, 700, 255, 256, 257, 100], runp=0.3)
+    out.append(("big-l", b, so, [(l, 3, 0.05, m, 0) for m in (REG, HPC) for l in (64, 127, 128, 200, 255)]))
+    # AVX-512 tail rule: S % 16 == 0 and neighbours, at very high density so every l-mer is a minimizer
+    lens = [31 + 15 + 16 * j for j in range(0, 20)] + [46, 47, 48, 62, 63, 64, 16, 31]
+    b, so = B.batch(lens)
+    out.append(("tail-rule", b, so, [(31, 2, 0.5, SIMD, 0), (31, 2, 1.0, SIMD, 0), (31, 2, 0.5, HPCSIMD, 0),
+                                     (31, 2, 1.0, HPCSIMD, 0), (31, 2, 0.5, SIMD, 1), (16, 1, 1.0, SIMD, 0),
+                                     (16, 1, 1.0, HPCSIMD, 0)]))
+    # dense selection, l sweep, several tiles
+    b, so = B.batch([20000, 20000, 9000])
+    par = []
+    for l in (1, 2, 5, 16, 31):
+        par += all_modes(l, 3, 0.5 if l > 2 else 1.0, nt2=(l == 31))
+    par += [(31, 5, 0.0, REG, 0), (31, 5, 0.0, HPCSIMD, 0), (31, 5, 1e-9, HPCSIMD, 0), (31, 1, 0.01, HPC, 0),
+            (31, 70, 0.05, HPC, 0)]
+    out.append(("dense", b, so, par))
+    return out

@@ -1,0 +1,61 @@
+"""CPU tier: the product's kernel sources, compiled by g++ onto host threads (tests/emu), against the oracle.
+This checks kernel LOGIC only (halos, tile stitching, look-back order, tail rules); the GPU tier repeats the
+same cases through the nvcc-built library."""
+import numpy as np
+import pytest
+
+from conftest import assert_batch_matches_oracle
+from parity_cases import cases
+
+
+def test_emulated_kernels_match_oracle(S, O, emu_ctx, batches, fixture_seq):
+    for label, bases, so, params in cases(batches, fixture_seq, scale=1):
+        for (l, k, d, mode, var) in params:
+            got = emu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)
+            assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
+
+
+def test_emulated_rle_matches_oracle(S, O, emu_ctx, batches, fixture_seq):
+    seqs = [fixture_seq[:30000], batches.seq(0), batches.seq(1), batches.seq(15), batches.seq(16), batches.seq(17),
+            batches.seq(9000, runp=0.8), np.full(10000, ord("A"), np.uint8), batches.seq(5000, alphabet=b"ACGTNacgt")]
+    bases, so = batches.pack(seqs)
+    h, p, off = emu_ctx.encode_rle(bases, so)
+    for i, s in enumerate(seqs):
+        eh, ep = O.encode_rle_simd(s)
+        a, b = int(off[i]), int(off[i + 1])
+        assert h[a:b].tobytes() == eh and np.array_equal(p[a:b], ep), i
+
+
+def test_split_invariance_emulated(S, O, emu_ctx, batches):
+    """Chunk-stitch invariance: a batch gives the same per-sequence results as its two halves."""
+    bases, so = batches.batch([9000, 150, 0, 20000, 31, 7000])
+    whole = emu_ctx.run(bases, so, 31, 5, 0.02, S.HashMode.HpcSimd)
+    cut = 3
+    left = emu_ctx.run(bases[:int(so[cut])], so[:cut + 1], 31, 5, 0.02, S.HashMode.HpcSimd)
+    right = emu_ctx.run(bases[int(so[cut]):], so[cut:] - so[cut], 31, 5, 0.02, S.HashMode.HpcSimd)
+    assert np.array_equal(whole.hash, np.concatenate([left.hash, right.hash]))
+    assert np.array_equal(whole.start, np.concatenate([left.start, right.start]))
+    assert np.array_equal(whole.end, np.concatenate([left.end, right.end]))
+
+
+def test_error_codes_mirror_reference_panics(S, emu_ctx):
+    b = np.frombuffer(b"ACGT" * 100, dtype=np.uint8)
+    so = np.array([0, 400], dtype=np.uint64)
+    with pytest.raises(S.S2KError) as e:       # assert!(k<=31), src/nthash_avx512_32.rs:33
+        emu_ctx.run(b, so, 32, 5, 0.1, S.HashMode.Simd)
+    assert e.value.status == -2
+    with pytest.raises(S.S2KError) as e:       # KSizeTooBig / assert!(k<256), src/nthash_hpc.rs:123-133
+        emu_ctx.run(b, so, 256, 5, 0.1, S.HashMode.Hpc)
+    assert e.value.status == -2
+    for bad in ((0, 5), (5, 0)):
+        with pytest.raises(S.S2KError) as e:
+            emu_ctx.run(b, so, bad[0], bad[1], 0.1, S.HashMode.Hpc)
+        assert e.value.status == -1
+    with pytest.raises(S.S2KError) as e:       # the 31-bit iterator only exists for the SIMD modes
+        emu_ctx.run(b, so, 31, 5, 0.1, S.HashMode.Hpc, S.HashVariant.NT2_31)
+    assert e.value.status == -1
+    with pytest.raises(S.S2KError) as e:
+        emu_ctx.run(b, np.array([0, 300, 200, 400], dtype=np.uint64), 5, 2, 0.1, S.HashMode.Hpc)
+    assert e.value.status == -5
+    empty = emu_ctx.run(b[:0], np.array([0], dtype=np.uint64), 5, 2, 0.1, S.HashMode.Hpc)
+    assert empty.n_items == 0 and empty.n_seqs == 0

@@ -1,0 +1,145 @@
+"""GPU tier (B200): the nvcc-built library through the C ABI, bit-exact against the CPU oracle.
+Small/medium sizes compare full item tuples per sequence; BASELINE-scale shapes are covered by per-read
+digests of full tuples on a slab plus size-independent properties (split invariance, order, offsets)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_batch_matches_oracle
+from parity_cases import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build(S, gpu_ctx):
+    assert S.LIB_PATH.exists() and gpu_ctx.lib.path == S.LIB_PATH
+    assert gpu_ctx.launch_count == 0
+
+
+def test_parity_cases_full_tuples(S, O, gpu_ctx, batches, fixture_seq):
+    n0 = gpu_ctx.launch_count
+    for label, bases, so, params in cases(batches, fixture_seq, scale=4):
+        for (l, k, d, mode, var) in params:
+            got = gpu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)
+            assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
+    assert gpu_ctx.launch_count > n0
+
+
+def test_reference_golden_vectors_through_the_abi(S, gpu_ctx, fixture_seq):
+    """tests/main.rs:41-57 (KAT-1) and the reference's own test structure (tests/main.rs:60-89)."""
+    from test_oracle_kats import KAT1
+    it = S.KminmersIterator(fixture_seq, 10, 5, 0.0001, S.HashMode.Regular, ctx=gpu_ctx)
+    assert [km.get_hash() for km in it] == KAT1
+    for l in (5, 7, 11, 17, 25, 31):
+        for k in (2, 5, 8):
+            a = list(S.KminmersIterator(fixture_seq, l, k, 0.01, S.HashMode.Regular, ctx=gpu_ctx))
+            b = list(S.KminmersIterator(fixture_seq, l, k, 0.01, S.HashMode.Simd, ctx=gpu_ctx))
+            c = list(S.KminmersIterator(fixture_seq, l, k, 0.01, S.HashMode.Hpc, ctx=gpu_ctx))
+            d = list(S.KminmersIterator(fixture_seq, l, k, 0.01, S.HashMode.HpcSimd, ctx=gpu_ctx))
+            assert a == b and c == d and len(a) > 0 and len(c) > 0
+
+
+def test_rle_primitives(S, O, gpu_ctx, batches, fixture_seq):
+    """tests/main.rs:76-78 on the GPU path."""
+    h, p = S.encode_rle_simd(fixture_seq, ctx=gpu_ctx)
+    eh, ep = O.encode_rle_simd(fixture_seq)
+    assert h == eh and np.array_equal(p, ep) and S.hpc(fixture_seq, ctx=gpu_ctx) == O.hpc(fixture_seq)
+    seqs = [batches.seq(n, runp=rp) for n, rp in [(0, 0), (1, 0), (15, 0), (16, 0), (17, 0), (100000, 0.7), (40000, 0)]]
+    seqs.append(np.full(70000, ord("A"), np.uint8))
+    bases, so = batches.pack(seqs)
+    hh, pp, off = gpu_ctx.encode_rle(bases, so)
+    for i, s in enumerate(seqs):
+        eh, ep = O.encode_rle_simd(s)
+        assert hh[int(off[i]):int(off[i + 1])].tobytes() == eh and np.array_equal(pp[int(off[i]):int(off[i + 1])], ep)
+
+
+@pytest.mark.parametrize("shape", ["hifi20k", "short150", "chromosome"])
+def test_synthetic_shapes_digest(S, O, gpu_ctx, shape):
+    """Synthetic reads of the BASELINE shapes (SURVEY.md 8d generator), every read verified through an
+    order-sensitive digest of its full (hash, start, end, rev) tuples computed by the oracle on all host cores."""
+    threads = os.cpu_count() or 1
+    if shape == "hifi20k":
+        L, n, seed, runs = 20000, 3000, 0x5EED0002, [(31, 5, 0.01, 3, 0), (31, 5, 0.01, 1, 0)]
+    elif shape == "short150":
+        L, n, seed, runs = 150, 400000, 0x5EED0003, [(31, 5, 0.01, 3, 0), (31, 5, 0.01, 1, 0), (31, 5, 0.01, 2, 0)]
+    else:
+        L, n, seed, runs = 30_000_000, 1, 0x5EED0004, [(31, 5, 0.01, 3, 1), (31, 5, 0.01, 2, 1), (31, 5, 0.01, 3, 0)]
+    bases = O.synth(seed, 0, L * n)
+    so = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+    for (l, k, d, mode, var) in runs:
+        got = gpu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var), copy=False)
+        want = O.batch(bases, so, l, k, d, mode, var, threads=threads, want_digest=True)
+        assert got.n_items == want["total"] and got.n_minimizers >= want["total_min"]
+        assert np.array_equal(np.diff(got.km_off), want["km_cnt"])
+        assert np.array_equal(got.min_cnt.astype(np.uint64), want["min_cnt"])
+        dg = O.digest_items(got.hash, got.start, got.end, got.rev, got.km_off)
+        assert np.array_equal(dg, want["digest"]), (shape, mode, var)
+        if got.n_items:
+            assert bool(np.all(got.start <= got.end))
+
+
+def test_kat9_first_synthetic_read(S, gpu_ctx, O):
+    rd = O.synth(0x5EED0002, 0, 20000)
+    so = np.array([0, 20000], dtype=np.uint64)
+    r = gpu_ctx.run(rd, so, 31, 5, 0.01, S.HashMode.HpcSimd)
+    assert (r.n_minimizers, r.n_items, int(r.hash.sum(dtype=np.uint64)), int(r.end.astype(np.uint64).sum())) == \
+        (270, 266, 11666637108378545117, 2831144)
+    r = gpu_ctx.run(rd, so, 31, 5, 0.01, S.HashMode.Simd, S.HashVariant.NT2_31)
+    assert (r.n_minimizers, r.n_items, int(r.hash.sum(dtype=np.uint64))) == (383, 379, 9878680082315566458)
+
+
+def test_device_api_and_full_scale_properties(S, O, gpu_ctx):
+    """Device-resident path at a BASELINE-scale shape (config 2 geometry: 20-kb reads, >2^30 bases so that the
+    launch is split into slabs): results equal the host-buffer path on a slab, are invariant to how the batch is
+    split, and satisfy order/offset properties; a sample of reads is checked tuple by tuple against the oracle."""
+    import torch
+    L, n = 20000, 60000                                   # 1.2 Gbp: crosses the 2^30-base slab boundary
+    seed = 0x5EED0002
+    dev = torch.device("cuda:0")
+    d_bases = torch.empty(L * n, dtype=torch.uint8, device=dev)
+    gpu_ctx.synth_device(seed, 0, L * n, d_bases.data_ptr())
+    d_so = (torch.arange(n + 1, dtype=torch.int64, device=dev) * L)
+    torch.cuda.synchronize()
+    assert bytes(d_bases[:64].cpu().numpy()) == b"CATACGACGGATAATATTGTCGGTACACATAGTGCCTGAGTATGTGTAGACGCCGACCATTATA"
+
+    def run(first_read, n_reads):
+        r = gpu_ctx.run_device(d_bases.data_ptr() + first_read * L, d_so.data_ptr(), n_reads, n_reads * L, 31, 5, 0.01,
+                               S.HashMode.HpcSimd)
+        t = lambda p, c, isz, dt: torch.as_tensor(S.DeviceArray(p, c * isz, "|u1"), device=dev).view(dt).clone()
+        return dict(n=int(r.n_items), hash=t(r.hash, r.n_items, 8, torch.int64), start=t(r.start, r.n_items, 4, torch.int32),
+                    end=t(r.end, r.n_items, 4, torch.int32), rev=t(r.rev, r.n_items, 1, torch.uint8),
+                    km_off=t(r.km_off, n_reads + 1, 8, torch.int64))
+
+    whole = run(0, n)
+    assert whole["n"] > 0 and int(whole["km_off"][-1]) == whole["n"]
+    assert bool((whole["km_off"][1:] >= whole["km_off"][:-1]).all())
+    assert bool((whole["start"] <= whole["end"]).all())
+    # split invariance at a read boundary that is not a tile/slab boundary
+    cut = 33333
+    left, right = run(0, cut), run(cut, n - cut)
+    for key in ("hash", "start", "end", "rev"):
+        assert torch.equal(whole[key], torch.cat([left[key], right[key]])), key
+    assert torch.equal(whole["km_off"][:cut + 1], left["km_off"])
+    # sample of reads against the oracle, including the reads around the slab boundary (2^30 / 20000 ~ 53687)
+    tile_reads = (131072 * 7936) // L
+    sample = [0, 1, 11, cut - 1, cut, tile_reads - 1, tile_reads, tile_reads + 1, n - 1]
+    km = whole["km_off"].cpu().numpy()
+    for rdx in sample:
+        a, b = int(km[rdx]), int(km[rdx + 1])
+        want = O.kminmers(O.synth(seed, rdx * L, L), 31, 5, 0.01, O.HPCSIMD)
+        assert b - a == len(want["hash"]), rdx
+        assert np.array_equal(whole["hash"][a:b].cpu().numpy().view(np.uint64), want["hash"]), rdx
+        assert np.array_equal(whole["start"][a:b].cpu().numpy().view(np.uint32), want["start"].astype(np.uint32)), rdx
+        assert np.array_equal(whole["end"][a:b].cpu().numpy().view(np.uint32), want["end"].astype(np.uint32)), rdx
+        assert np.array_equal(whole["rev"][a:b].cpu().numpy(), want["rev"]), rdx
+
+
+def test_error_codes(S, gpu_ctx):
+    b = np.frombuffer(b"ACGT" * 100, dtype=np.uint8)
+    so = np.array([0, 400], dtype=np.uint64)
+    for args, status in [((32, 5, 0.1, S.HashMode.Simd), -2), ((256, 5, 0.1, S.HashMode.Hpc), -2),
+                         ((0, 5, 0.1, S.HashMode.Hpc), -1), ((5, 0, 0.1, S.HashMode.Hpc), -1)]:
+        with pytest.raises(S.S2KError) as e:
+            gpu_ctx.run(b, so, *args)
+        assert e.value.status == status
