@@ -85,7 +85,7 @@ struct s2k_ctx {
     double rate_hint = 0.0;         // observed minimizers per base (grow-only)
     // device buffers
     Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_hpc_off, d_km_off, d_min_cnt;
-    Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos;
+    Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr;
     // pinned host result buffers
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
@@ -141,7 +141,7 @@ struct Plan {
     bool hpc, simd, w31, quirk;
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
-    uint8_t lut[256];
+    uint8_t lut[256];   // raw byte -> 8 * base class
     uint2 xy[64];
 };
 
@@ -165,7 +165,7 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     P.need = P.l - 1 + P.d;
     P.quirk = P.simd && !P.w31;
     P.halo = P.need >= 128 ? 512u : 256u;
-    P.tile = (uint32_t)WIN - P.halo;
+    P.tile = P.hpc ? (uint32_t)WIN - P.halo : std::min<uint32_t>((uint32_t)CAP, (uint32_t)WIN - P.halo);
     const uint32_t bs = bound_scalar(p->density);
     uint64_t excl;                                   // select iff hash < excl
     if (P.simd) { uint32_t b = bound_simd(bs); if (P.w31) b /= 2; excl = b; }
@@ -182,10 +182,10 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     h[5] = rc[5] = 1;
     if (P.simd) {                                    // low nibble, src/nthash_avx512_32.rs:178-193
         static const uint8_t nib[16] = {4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4};
-        for (int i = 0; i < 256; ++i) P.lut[i] = nib[i & 15];
+        for (int i = 0; i < 256; ++i) P.lut[i] = (uint8_t)(8 * nib[i & 15]);
     } else {                                         // src/nthash_hpc.rs:29-49
-        for (int i = 0; i < 256; ++i) P.lut[i] = 5;
-        P.lut['A'] = 0; P.lut['C'] = 1; P.lut['G'] = 2; P.lut['T'] = 3; P.lut['N'] = 4;
+        for (int i = 0; i < 256; ++i) P.lut[i] = 8 * 5;
+        P.lut['A'] = 8 * 0; P.lut['C'] = 8 * 1; P.lut['G'] = 8 * 2; P.lut['T'] = 8 * 3; P.lut['N'] = 8 * 4;
     }
     for (int o = 0; o < 8; ++o)
         for (int i = 0; i < 8; ++i) {
@@ -197,7 +197,7 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
 
 template <typename T> T *ptr(Buf &b) { return reinterpret_cast<T *>(b.p); }
 
-constexpr uint64_t SLAB_TILES = 131072;              // tiles per minimizer launch (< 2^30 bases: 31-bit look-back fields)
+constexpr uint64_t SLAB_TILES = 65536;               // tiles per minimizer launch (< 2^30 bases: 31-bit look-back fields)
 
 int set_attrs(s2k_ctx *ctx)
 {
@@ -261,6 +261,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     const uint64_t n_slabs = (n_bases + slab_len - 1) / slab_len;
     const uint64_t max_tiles = std::min<uint64_t>(SLAB_TILES, (n_bases + P.tile - 1) / P.tile);
     if ((rc = ensure(ctx, ctx->d_tile_lb, (max_tiles + 1) * 4, false))) return rc;
+    const int max_grid = ctx->sm_count * 3;
+    if ((rc = ensure(ctx, ctx->d_hscr, (size_t)max_grid * WIN * 4, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_status, std::max<uint64_t>(max_tiles, (n_seqs + RT * RPT - 1) / (RT * RPT)) * 8 + 8, false))) return rc;
 
     // capacity of the minimizer stream: expected 2*density*(kept bases), with head room; grown and rerun on overflow
@@ -287,6 +289,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
             A.min_off = ptr<uint64_t>(ctx->d_min_off);
             A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
             A.err = reinterpret_cast<uint32_t *>(small + 5);
+            A.hscr = ptr<uint32_t>(ctx->d_hscr);
             A.n_seqs = n_seqs; A.n_bases = n_bases;
             A.slab_begin = s * slab_len; A.slab_end = std::min(n_bases, (s + 1) * slab_len);
             A.n_tiles = (uint32_t)((A.slab_end - A.slab_begin + P.tile - 1) / P.tile);
@@ -298,7 +301,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
             CU(cudaMemsetAsync(A.ticket, 0, 4, st));
             S2K_LAUNCH(k_tile_bounds, (A.n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, A.slab_begin,
                        A.slab_end, P.tile, A.n_tiles, ptr<uint32_t>(ctx->d_tile_lb));
-            const int grid = (int)std::min<uint64_t>(A.n_tiles, (uint64_t)ctx->sm_count * 3);
+            const int grid = (int)std::min<uint64_t>(A.n_tiles, (uint64_t)max_grid);
             const size_t smem = sizeof(Smem);
             Timing &T = ctx->tm;
             const bool rec = T.enabled && T.n < 64;
@@ -457,7 +460,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     Buf *all[] = {&ctx->d_bases, &ctx->d_seq_off, &ctx->d_tile_lb, &ctx->d_status, &ctx->d_small, &ctx->d_mins,
                   &ctx->d_min_off, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
-                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
+                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos};
     for (Buf *b : all) release(*b);

@@ -38,14 +38,16 @@ namespace s2k {
 
 // ------------------------------------------------------------------------------------------------ geometry
 constexpr int NT    = 256;          // threads per CTA
-constexpr int CH    = 32;           // owner positions per thread in the hash phase
-constexpr int WIN   = NT * CH;      // raw bases staged per tile (left halo + tile)
+constexpr int RAWPT = 64;           // raw bases per thread in the keep/compaction phase
+constexpr int WIN   = NT * RAWPT;   // raw bases staged per tile (left halo + tile)
+constexpr int NCHUNK = WIN / 32;    // 32-base chunks per window
+constexpr int CH    = 60;           // owner positions per thread in the hash phase: 15 words, an odd word stride,
+                                    // so the per-lane byte streams of a warp fall into 32 different banks
+constexpr int CAP   = NT * CH;      // owners hashed per pass (a second pass covers tiles that compress badly)
 constexpr int XB    = 256;          // capacity of the left context, in kept (HPC) bases
-constexpr int XC    = XB / CH;      // ... in columns of the transposed code array
-constexpr int NTP   = NT + XC + 4;  // column pitch of the transposed code array (268 = 4*67: conflict-free rows)
-constexpr int NWORD = WIN / 32;     // 32-base chunks per window == NT
-constexpr int OOW   = NT + XC + 1;  // words of the owner-space flag bitmaps
-constexpr int ZCLS  = 4;            // base class whose forward and reverse seeds are both 0
+constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
+constexpr int HL    = 1024;         // hit-list entries emitted per round
+constexpr int ZC8   = 4 * 8;        // pre-scaled base class whose forward and reverse seeds are both 0
 
 constexpr uint64_t FLAG_AGG  = 1ull << 62;
 constexpr uint64_t FLAG_INCL = 2ull << 62;
@@ -66,28 +68,28 @@ struct K1Args {
     uint64_t  min_cap;
     uint64_t *min_off;           // n_seqs + 1
     uint64_t *hpc_off;           // n_seqs + 1 or null
+    uint32_t *hscr;              // gridDim.x * WIN words: per-CTA stash of selected hashes (stays in L2)
     uint32_t *err;
     uint64_t  n_seqs, n_bases, slab_begin, slab_end;
     uint32_t  n_tiles, tile, halo;
     uint32_t  l, d, need, thr;
-    uint8_t   cls_lut[256];      // raw byte -> base class (0..5)
+    uint8_t   cls_lut[256];      // raw byte -> 8 * base class (classes 0..5)
     uint2     xy[64];            // [out*8+in] -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
 };
 
 struct Smem {
-    uint8_t  raw[16 + WIN];
-    uint8_t  code[32 * NTP];
-    uint32_t hh[WIN];
-    uint32_t keepw[NWORD + 1];
-    uint32_t qoff[NWORD + 1];
-    uint32_t startw[NWORD];
-    uint32_t shortw[NWORD];
-    uint32_t f1[OOW + 1];
-    uint32_t f2[OOW + 1];
-    uint32_t hitw[NT + 1];
-    uint32_t hitpre[NT + 1];
-    uint32_t ctxpos[XB];
+    uint8_t  code[XB + WIN + 128];           // 8*class of every kept base, index XB + (kept index in the window)
+    unsigned long long hitw[2][NT + 1];      // per pass, per thread: selected owners (bit i = owner 60*t + i)
+    uint32_t hitpre[2][NT + 1];              // ... and how many hits precede that thread in the tile
+    uint32_t keepw[NCHUNK + 1];              // keep mask per 32-base chunk
+    uint32_t qoff[NCHUNK + 1];               // kept bases before the chunk
+    uint32_t startw[NCHUNK];                 // raw-space bitmap: sequence starts
+    uint32_t shortw[NCHUNK];                 // ... of sequences with len <= l
+    uint32_t f1[FW];                         // owner-space bitmap: kept bases that start a sequence
+    uint32_t f2[FW];                         // ... of sequences with len <= l
+    uint32_t ctxpos[XB];                     // walk-back context: distance below W0
     uint2    xy[64];
+    uint16_t hl[HL];
     uint8_t  lut[256];
     uint32_t wsum[8];
     uint32_t tile_id, hk, min_ex, kept_ex;
@@ -129,7 +131,6 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v)
     return v;
 }
 // Exclusive block scan of one uint32 per thread (NT threads). Returns exclusive prefix; total via out-param.
-// Uses S.wsum; callers must not touch wsum until the trailing barrier inside has been passed.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, uint32_t &total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -148,10 +149,16 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, 
     return pre + incl - v;
 }
 __device__ __forceinline__ uint32_t lowmask(uint32_t n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
-__device__ __forceinline__ int nth_set_bit(uint32_t w, int r)
+__device__ __forceinline__ unsigned long long lowmask64(uint32_t n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
+__device__ __forceinline__ int nth_set_bit(uint32_t w, int r)      // position of the r-th (0-based) set bit
 {
-    for (int t = 0; t < r; ++t) w &= w - 1;
-    return __ffs(w) - 1;
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int c = __popc(w & ((1u << s) - 1u));
+        if (r >= c) { r -= c; pos += s; w >>= s; }
+    }
+    return pos;
 }
 template <bool W31> __device__ __forceinline__ uint32_t rol1(uint32_t x)
 {
@@ -163,16 +170,19 @@ template <bool W31> __device__ __forceinline__ uint32_t ror1(uint32_t x)
     if (W31) return (x >> 1) | ((x & 1u) << 30);
     return __funnelshift_r(x, x, 1);
 }
-__device__ __forceinline__ int code_idx(int ee) { return (ee & 31) * NTP + (ee >> 5); }
+__device__ __forceinline__ uint2 xy_at(const Smem &S, uint32_t out8, uint32_t in8)
+{
+    return *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(S.xy) + (out8 << 3) + in8);
+}
 
 // Original-space position (global index into `bases`) of the kept base with window index q
 // (q < 0: context gathered by the walk-back).
 __device__ __forceinline__ int64_t pos_of(const Smem &S, int64_t W0, int q)
 {
     if (q < 0) return W0 - (int64_t)S.ctxpos[-1 - q];
-    int lo = 0, hi = NT;                    // qoff[lo] <= q < qoff[hi]
+    int lo = 0, hi = NCHUNK;                // qoff[lo] <= q < qoff[hi]
     while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
+        const int mid = (lo + hi) >> 1;
         if ((int)S.qoff[mid] <= q) lo = mid; else hi = mid;
     }
     return W0 + 32 * lo + nth_set_bit(S.keepw[lo], q - (int)S.qoff[lo]);
@@ -195,6 +205,19 @@ __global__ void k_tile_bounds(const uint64_t *__restrict__ seq_off, uint64_t n_s
 }
 
 // ------------------------------------------------------------------------------------------------ minimizers
+// One tile = `tile` raw bases plus a left halo.  Per tile:
+//   S2  sequence starts falling into the window -> raw-space bitmaps
+//   S3  64 raw bases per thread straight from global into registers; keep mask (byte != previous byte, or a
+//       sequence start); block scan of kept counts
+//   S4  branch-free compaction of the kept bases' classes into S.code (HPC order); start flags -> owner space;
+//       if the halo holds fewer than l-1(+1) kept bases of the current sequence, warp 0 walks further back
+//   S5  every kept base of the tile "owns" one l-mer (the one it completes).  60 owners per thread: l-1 warm-up
+//       steps, then one rolling step per owner: 2 byte loads, one table load, 2 rotates, 2 three-input XORs,
+//       min, compare.  Selected hashes go to a per-CTA scratch that lives in L2.
+//   S6  block scan of hit counts, decoupled look-back across tiles (one 64-bit word: kept count | hit count)
+//   S7  hits are listed in order in shared memory and handed out one per thread: positions by rank/select on
+//       the keep masks, sequence index by binary search of seq_off, one 16-byte record store per minimizer
+//   S8  per-sequence offsets (minimizers, kept bases) for every sequence that starts in the tile
 template <bool HPC, bool W31>
 __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1Args A)
 {
@@ -202,14 +225,17 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = (int)A.l, d = (int)A.d;
+    uint32_t *const hs = A.hscr + (size_t)blockIdx.x * WIN;
 
     for (int i = tid; i < 256; i += NT) S.lut[i] = A.cls_lut[i];
     if (tid < 64) S.xy[tid] = A.xy[tid];
-    for (int i = tid; i < 32 * NTP; i += NT) S.code[i] = ZCLS;
+    for (int i = tid; i < XB + WIN + 128; i += NT) S.code[i] = ZC8;
 
     for (;;) {
         __syncthreads();                                   // everyone is done with the previous tile
         if (tid == 0) S.tile_id = atomicAdd(A.ticket, 1u);
+        for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
+        for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
         __syncthreads();
         const uint32_t t = S.tile_id;
         if (t >= A.n_tiles) break;
@@ -221,27 +247,29 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         const uint32_t lb = A.tile_lb[t];
         const uint32_t ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
 
-        // ---- S1: stage raw bytes [W0-16, W0+WIN); bytes outside [0, n_bases) read as 0
-        for (int v = tid; v < (WIN + 16) / 16; v += NT) {
-            const int64_t g = W0 - 16 + (int64_t)v * 16;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (g >= 0 && g + 16 <= (int64_t)A.n_bases) {
-                val = __ldg(reinterpret_cast<const uint4 *>(A.bases + g));
-            } else if (g + 16 > 0 && g < (int64_t)A.n_bases) {
-                uint32_t w[4] = {0, 0, 0, 0};
-                for (int j = 0; j < 16; ++j) {
-                    const int64_t gg = g + j;
-                    if (gg >= 0 && gg < (int64_t)A.n_bases) w[j >> 2] |= (uint32_t)A.bases[gg] << (8 * (j & 3));
-                }
-                val = make_uint4(w[0], w[1], w[2], w[3]);
+        // ---- S3a: this thread's 64 raw bases, global -> registers (issued first: the latency overlaps S2)
+        const int64_t g0 = W0 + RAWPT * tid;
+        uint32_t w[16];
+        if (g0 >= 0 && g0 + RAWPT <= (int64_t)A.n_bases) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.bases + g0);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint4 x = __ldg(src + v);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
             }
-            *reinterpret_cast<uint4 *>(S.raw + v * 16) = val;
+        } else {
+#pragma unroll
+            for (int v = 0; v < 16; ++v) {
+                uint32_t x = 0;
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t gg = g0 + 4 * v + j;
+                    if (gg >= 0 && gg < (int64_t)A.n_bases) x |= (uint32_t)A.bases[gg] << (8 * j);
+                }
+                w[v] = x;
+            }
         }
-        for (int i = tid; i < NWORD; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
-        for (int i = tid; i < OOW + 1; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
-        __syncthreads();
 
-        // ---- S2: sequence starts inside the tile (and the start of the sequence containing T0, if staged)
+        // ---- S2: sequence starts inside the tile (and the start of the sequence containing T0, if in the window)
         for (uint32_t i = lb + tid; i < ub; i += NT) {
             const uint64_t so = A.seq_off[i];
             if (so < (uint64_t)T1) {
@@ -266,61 +294,61 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         }
         __syncthreads();
 
-        // ---- S3: keep mask of this thread's 32 raw bases, block scan of kept counts
-        uint32_t w[8];
-        {
-            const uint4 a = *reinterpret_cast<const uint4 *>(S.raw + 16 + 32 * tid);
-            const uint4 b = *reinterpret_cast<const uint4 *>(S.raw + 32 + 32 * tid);
-            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-        }
-        uint32_t keep;
+        // ---- S3b: keep mask, block scan of kept counts
+        uint32_t klo, khi;
         if (HPC) {
-            uint32_t prevb = S.raw[16 + 32 * tid - 1];
-            keep = 0;
+            uint32_t prevb = __shfl_up_sync(0xffffffffu, w[15] >> 24, 1);
+            if (lane == 0) prevb = (g0 > 0 && g0 <= (int64_t)A.n_bases) ? A.bases[g0 - 1] : 0u;
+            uint32_t kk[2] = {0u, 0u};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 const uint32_t sh = (w[i] << 8) | prevb;
                 prevb = w[i] >> 24;
                 const uint32_t neq = __vcmpne4(w[i], sh);
-                keep |= (((neq & 0x08040201u) * 0x01010101u) >> 24) << (4 * i);
+                kk[i >> 3] |= (((neq & 0x08040201u) * 0x01010101u) >> 24) << (4 * (i & 7));
             }
-            keep |= S.startw[tid];
+            klo = kk[0] | S.startw[2 * tid];
+            khi = kk[1] | S.startw[2 * tid + 1];
         } else {
-            keep = 0xffffffffu;
+            klo = khi = 0xffffffffu;
         }
         {
-            const int64_t g0 = W0 + 32 * tid;
-            uint32_t vmask = 0xffffffffu;
-            if (g0 < 0) vmask = (g0 <= -32) ? 0u : (0xffffffffu << (int)(-g0));
+            unsigned long long vmask = ~0ull;
+            if (g0 < 0) vmask = (g0 <= -64) ? 0ull : (~0ull << (int)(-g0));
             const int64_t rem = T1 - g0;
-            if (rem <= 0) vmask = 0u; else if (rem < 32) vmask &= (1u << (int)rem) - 1u;
-            keep &= vmask;
+            if (rem <= 0) vmask = 0ull; else if (rem < 64) vmask &= (1ull << (int)rem) - 1ull;
+            klo &= (uint32_t)vmask; khi &= (uint32_t)(vmask >> 32);
         }
+        const uint32_t clo = __popc(klo);
         uint32_t wk;
-        const uint32_t q = block_excl_scan(__popc(keep), S.wsum, wk);
-        S.keepw[tid] = keep;
-        S.qoff[tid] = q;
-        if (tid == NT - 1) { S.qoff[NT] = wk; S.keepw[NT] = 0; }
-        if (tid == (int)(A.halo >> 5)) S.hk = q;
+        const uint32_t q = block_excl_scan(clo + __popc(khi), S.wsum, wk);
+        S.keepw[2 * tid] = klo; S.keepw[2 * tid + 1] = khi;
+        S.qoff[2 * tid] = q; S.qoff[2 * tid + 1] = q + clo;
+        if (tid == NT - 1) { S.qoff[NCHUNK] = wk; S.keepw[NCHUNK] = 0; }
+        if (tid == (int)(A.halo >> 6)) S.hk = ((A.halo >> 5) & 1u) ? q + clo : q;
+
+        // ---- S4: compaction (predicated byte stores in HPC order)
+        {
+            uint8_t *cp = S.code + XB + q;
+#pragma unroll
+            for (int b = 0; b < 64; ++b) {
+                const uint32_t kb = (b < 32 ? (klo >> b) : (khi >> (b - 32))) & 1u;
+                if (kb) { *cp = S.lut[(w[b >> 2] >> (8 * (b & 3))) & 0xffu]; ++cp; }
+            }
+        }
         __syncthreads();
         const uint32_t hk = S.hk;
-
-        // ---- S4: compaction of base classes into the transposed code array, start flags into owner space
-        {
-            int ee = (int)q - (int)hk + d + 256;           // code index of this thread's first kept base
-            const uint32_t sw = S.startw[tid] & keep, sh2 = S.shortw[tid];
-#pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                if ((keep >> b) & 1u) {
-                    if (ee >= 0) S.code[code_idx(ee)] = S.lut[(w[b >> 2] >> (8 * (b & 3))) & 0xffu];
-                    if ((sw >> b) & 1u) {
-                        const int oo = ee - d;
-                        if (oo >= 0) {
-                            atomicOr(&S.f1[oo >> 5], 1u << (oo & 31));
-                            if ((sh2 >> b) & 1u) atomicOr(&S.f2[oo >> 5], 1u << (oo & 31));
-                        }
-                    }
-                    ++ee;
+        {   // sequence starts among this thread's kept bases -> owner-space flags (rare)
+            const unsigned long long keep = ((unsigned long long)khi << 32) | klo;
+            unsigned long long sw = (((unsigned long long)S.startw[2 * tid + 1] << 32) | S.startw[2 * tid]) & keep;
+            const unsigned long long sh2 = ((unsigned long long)S.shortw[2 * tid + 1] << 32) | S.shortw[2 * tid];
+            while (sw) {
+                const int b = __ffsll((long long)sw) - 1;
+                sw &= sw - 1;
+                const int oo = (int)q + __popcll(keep & lowmask64(b)) - (int)hk + XB;
+                if (oo >= 0) {
+                    atomicOr(&S.f1[oo >> 5], 1u << (oo & 31));
+                    if ((sh2 >> b) & 1ull) atomicOr(&S.f2[oo >> 5], 1u << (oo & 31));
                 }
             }
         }
@@ -342,10 +370,9 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
                 const uint32_t rank = __popc(above);
                 if (kp && rank < remaining) {
                     const uint32_t slot = taken + rank;            // 0 = nearest to the window
-                    const int ee = -1 - (int)slot - (int)hk + d + 256;
-                    if (ee >= 0) S.code[code_idx(ee)] = S.lut[b];
+                    S.code[XB - 1 - (int)slot] = S.lut[b];
                     S.ctxpos[slot] = (uint32_t)(W0 - g);
-                    if (g == s0) { const int oo = ee - d; if (oo >= 0) atomicOr(&S.f1[oo >> 5], 1u << (oo & 31)); }
+                    if (g == s0) { const int oo = XB - 1 - (int)slot - (int)hk; if (oo >= 0) atomicOr(&S.f1[oo >> 5], 1u << (oo & 31)); }
                 }
                 const uint32_t c = min((uint32_t)__popc(m), remaining);
                 taken += c; remaining -= c; hi = lo;
@@ -353,64 +380,66 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         }
         __syncthreads();
 
-        // ---- S5: rolling canonical ntHash over this thread's 32 owner positions
-        const uint32_t n_own = wk - hk;                   // kept bases in [T0, T1): one l-mer is owned by each
-        const int ubase = 32 * tid;
-        uint32_t mask = 0;
-        if ((uint32_t)ubase < n_own) {
-            const int n_u = min(32, (int)n_own - ubase);
-            // owners invalidated by sequence starts: every start f kills owners [f, f+l-2+d] (+1 if len<=l)
-            uint32_t invalid = 0;
-            {
-                const int L1 = l - 1 + d;
-                const int w_hi = tid + XC, w_lo = (ubase + 256 - L1 - 1) >> 5;
-                for (int wi = w_lo; wi <= w_hi; ++wi) {
-                    uint32_t fw = S.f1[wi];
-                    if (fw) {
-                        const uint32_t sw2 = S.f2[wi];
-                        while (fw) {
-                            const int b = __ffs(fw) - 1;
-                            fw &= fw - 1;
-                            int lo = wi * 32 + b - (ubase + 256);
-                            int hi = lo + L1 + (int)((sw2 >> b) & 1u);
-                            lo = max(lo, 0); hi = min(hi, 32);
-                            if (hi > lo) invalid |= lowmask(hi - lo) << lo;
+        // ---- S5 + S6a: rolling canonical ntHash over the owners, CAP per pass; block scan of hit counts
+        const uint32_t n_own = wk - hk;                   // kept bases in [T0, T1): each completes one l-mer
+        uint32_t tile_min = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            unsigned long long mask = 0ull;
+            const int v0 = pass * CAP + CH * tid;
+            if ((uint32_t)(pass * CAP) < n_own) {          // uniform
+                if ((uint32_t)v0 < n_own) {
+                    const int n_u = min(CH, (int)n_own - v0);
+                    // owners invalidated by sequence starts: a start f kills owners [f, f+l-2+d] (+1 if len<=l)
+                    unsigned long long invalid = 0ull;
+                    {
+                        const int L1 = l - 1 + d, o0 = v0 + XB;
+                        const int w_hi = (o0 + CH - 1) >> 5, w_lo = (o0 - L1 - 1) >> 5;
+                        for (int wi = w_lo; wi <= w_hi; ++wi) {
+                            uint32_t fw = S.f1[wi];
+                            if (fw) {
+                                const uint32_t sw2 = S.f2[wi];
+                                while (fw) {
+                                    const int b = __ffs(fw) - 1;
+                                    fw &= fw - 1;
+                                    int lo = wi * 32 + b - o0;
+                                    int hi = lo + L1 + (int)((sw2 >> b) & 1u);
+                                    lo = max(lo, 0); hi = min(hi, 64);
+                                    if (hi > lo) invalid |= lowmask64(hi - lo) << lo;
+                                }
+                            }
                         }
                     }
-                }
-            }
-            uint32_t fh = 0, rh = 0;
-            {
-                int ee = ubase + 256 - l + 1;              // warm-up: first l-1 bases of owner 0's l-mer
-                for (int j = 0; j < l - 1; ++j, ++ee) {
-                    const uint32_t in = S.code[code_idx(ee)];
-                    const uint2 tt = S.xy[ZCLS * 8 + in];
-                    fh = rol1<W31>(fh) ^ tt.x;
-                    rh = ror1<W31>(rh) ^ tt.y;
-                }
-            }
-            const uint8_t *cin = S.code + tid + XC;
-            const int eo = ubase + 256 - l;
+                    const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer
+                    uint32_t fh = 0, rh = 0;
+                    for (int j = 1 - l; j < 0; ++j) {                  // warm-up: first l-1 bases of owner 0's l-mer
+                        const uint2 tt = xy_at(S, ZC8, cb[j]);
+                        fh = rol1<W31>(fh) ^ tt.x;
+                        rh = ror1<W31>(rh) ^ tt.y;
+                    }
+                    const uint8_t *co = cb - l;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t in = cin[i * NTP];
-                uint32_t out = ZCLS;
-                if (i > 0) out = S.code[code_idx(eo + i)];
-                const uint2 tt = S.xy[out * 8 + in];
-                fh = rol1<W31>(fh) ^ tt.x;
-                rh = ror1<W31>(rh) ^ tt.y;
-                const uint32_t h = min(fh, rh);
-                if (h <= A.thr && i < n_u) { mask |= 1u << i; S.hh[ubase + i] = h; }
+                    for (int i = 0; i < CH; ++i) {
+                        const uint32_t in8 = cb[i];
+                        const uint32_t out8 = i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8;
+                        const uint2 tt = xy_at(S, out8, in8);
+                        fh = rol1<W31>(fh) ^ tt.x;
+                        rh = ror1<W31>(rh) ^ tt.y;
+                        const uint32_t h = min(fh, rh);
+                        if (h <= A.thr && i < n_u) { mask |= 1ull << i; hs[v0 + i] = h; }
+                    }
+                    mask &= ~invalid;
+                }
             }
-            mask &= ~invalid;
+            uint32_t tot;
+            const uint32_t ex = block_excl_scan(__popcll(mask), S.wsum, tot);
+            S.hitw[pass][tid] = mask;
+            S.hitpre[pass][tid] = tile_min + ex;
+            tile_min += tot;
+            if (tid == NT - 1) { S.hitw[pass][NT] = 0ull; S.hitpre[pass][NT] = tile_min; }
         }
 
-        // ---- S6: ordered placement: block scan of hit counts, decoupled look-back across tiles
-        uint32_t tile_min;
-        const uint32_t hpre = block_excl_scan(__popc(mask), S.wsum, tile_min);
-        S.hitw[tid] = mask;
-        S.hitpre[tid] = hpre;
-        if (tid == NT - 1) { S.hitpre[NT] = tile_min; S.hitw[NT] = 0; }
+        // ---- S6b: decoupled look-back across tiles
         if (warp == 0) {
             const uint64_t agg = ((uint64_t)n_own << 31) | (uint64_t)tile_min;
             uint64_t excl = 0;
@@ -448,14 +477,26 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         const uint64_t min_base = A.carry_in[0] + S.min_ex;
         const uint64_t kept_base = A.carry_in[1] + S.kept_ex;
 
-        // ---- S7: emit minimizer records in order
-        {
-            uint32_t m = mask, kk = 0;
-            while (m) {
-                const int i = __ffs(m) - 1;
-                m &= m - 1;
-                const int qo = (int)hk + ubase + i;        // window index of the owner base
-                const uint32_t h = S.hh[ubase + i];
+        // ---- S7: ordered hit list in shared memory, then one thread per minimizer
+        for (uint32_t base = 0; base < tile_min; base += HL) {
+            if (base) __syncthreads();                     // previous round has been consumed
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                unsigned long long m = S.hitw[pass][tid];
+                uint32_t o = S.hitpre[pass][tid];
+                while (m) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if (o >= base && o < base + HL) S.hl[o - base] = (uint16_t)(pass * CAP + CH * tid + i);
+                    ++o;
+                }
+            }
+            __syncthreads();
+            const uint32_t n_round = min((uint32_t)HL, tile_min - base);
+            for (uint32_t j = tid; j < n_round; j += NT) {
+                const int v = S.hl[j];
+                const int qo = (int)hk + v;                // window index of the owner base
+                const uint32_t h = hs[v];
                 const int64_t g_own = pos_of(S, W0, qo);
                 const int64_t g_start = pos_of(S, W0, qo - (l - 1 + d));
                 uint32_t lo = lb, hi = ub;                 // first i in [lb,ub) with seq_off[i] > g_own
@@ -465,13 +506,12 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
                 }
                 const uint32_t rid = lo - 1;
                 const uint64_t so = A.seq_off[rid];
-                const uint64_t idx = min_base + hpre + kk;
+                const uint64_t idx = min_base + base + j;
                 if (idx < A.min_cap)
                     A.min_out[idx] = make_uint4(h, (uint32_t)((uint64_t)g_start - so),
                                                 (uint32_t)((uint64_t)g_own - (uint64_t)d - so), rid);
                 else
                     atomicOr(A.err, ERR_CAP);
-                ++kk;
             }
         }
         // ---- S8: per-sequence offsets for every sequence starting in this tile
@@ -480,7 +520,9 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
             const uint32_t x = (uint32_t)((int64_t)so - W0);
             const uint32_t qx = S.qoff[x >> 5] + __popc(S.keepw[x >> 5] & lowmask(x & 31));
             const uint32_t v = qx - hk;
-            const uint32_t hb = S.hitpre[v >> 5] + __popc(S.hitw[v >> 5] & lowmask(v & 31));
+            const uint32_t pass = v >= (uint32_t)CAP ? 1u : 0u;
+            const uint32_t vv = v - pass * CAP, u = vv / CH, bit = vv - u * CH;
+            const uint32_t hb = S.hitpre[pass][u] + __popcll(S.hitw[pass][u] & lowmask64(bit));
             A.min_off[i] = min_base + hb;
             if (A.hpc_off) A.hpc_off[i] = kept_base + v;
         }

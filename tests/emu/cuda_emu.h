@@ -124,6 +124,8 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline unsigned __vcmpne4(unsigned a, unsigned b)
 {
     unsigned r = 0;

@@ -37,6 +37,13 @@ def cases(B, fixture_seq, scale=1):
     s1 = np.concatenate(parts)
     b, so = B.pack([s1, B.seq(100), s1[::-1].copy(), np.full(8000, ord("C"), np.uint8), B.seq(500)])
     out.append(("homopolymers", b, so, all_modes(31, 5, 0.05) + all_modes(7, 2, 0.2, nt2=False)))
+    # sequences that do not compress at all in HPC space (more owners per tile than one hash pass covers)
+    norun = B.seq(50000)
+    for i in range(1, len(norun)):
+        if norun[i] == norun[i - 1]:
+            norun[i] = b"ACGT"[(b"ACGT".index(int(norun[i])) + 1 + int(rng.integers(0, 3))) % 4]
+    b, so = B.pack([np.frombuffer(b"ACGT" * 10000, dtype=np.uint8).copy(), norun, B.seq(3000)])
+    out.append(("incompressible", b, so, all_modes(31, 5, 0.02, nt2=False) + [(31, 3, 0.5, HPCSIMD, 0), (31, 3, 0.5, HPC, 0)]))
     # non-ACGT bytes: N, lower case, IUPAC, junk (scalar table vs nibble table)
     b, so = B.batch([3000, 5000, 100, 20000], alphabet=b"ACGTNacgtnXRY-")
     out.append(("non-ACGT", b, so, all_modes(21, 4, 0.1)))

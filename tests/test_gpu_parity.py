@@ -122,7 +122,7 @@ def test_device_api_and_full_scale_properties(S, O, gpu_ctx):
         assert torch.equal(whole[key], torch.cat([left[key], right[key]])), key
     assert torch.equal(whole["km_off"][:cut + 1], left["km_off"])
     # sample of reads against the oracle, including the reads around the slab boundary (2^30 / 20000 ~ 53687)
-    tile_reads = (131072 * 7936) // L
+    tile_reads = (65536 * 16128) // L
     sample = [0, 1, 11, cut - 1, cut, tile_reads - 1, tile_reads, tile_reads + 1, n - 1]
     km = whole["km_off"].cpu().numpy()
     for rdx in sample:
