@@ -85,7 +85,7 @@ struct s2k_ctx {
     double rate_hint = 0.0;         // observed minimizers per base (grow-only)
     // device buffers
     Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_hpc_off, d_km_off, d_min_cnt;
-    Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr;
+    Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr, d_tmp, d_tile_info, d_tile_base;
     // pinned host result buffers
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
@@ -197,7 +197,6 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
 
 template <typename T> T *ptr(Buf &b) { return reinterpret_cast<T *>(b.p); }
 
-constexpr uint64_t SLAB_TILES = 65536;               // tiles per minimizer launch (< 2^30 bases: 31-bit look-back fields)
 
 int set_attrs(s2k_ctx *ctx)
 {
@@ -222,7 +221,7 @@ void timing_prepare(s2k_ctx *ctx)
     T.n = 0;
 }
 
-// d_small layout (uint64 words): [0..1] carry A, [2..3] carry B, [4] ticket(u32), [5] err(u32), [6] ticket2(u32)
+// d_small layout (uint64 words): [0] record cursor, [4] ticket(u32), [5] err(u32), [6] ticket2(u32)
 // Runs the whole device pipeline on `st`.  On return the totals have been read back (one sync).
 int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs, uint64_t n_bases,
                const Plan &P, cudaStream_t st, s2k_result *out)
@@ -257,13 +256,15 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         return S2K_OK;
     }
 
-    const uint64_t slab_len = SLAB_TILES * (uint64_t)P.tile;
-    const uint64_t n_slabs = (n_bases + slab_len - 1) / slab_len;
-    const uint64_t max_tiles = std::min<uint64_t>(SLAB_TILES, (n_bases + P.tile - 1) / P.tile);
-    if ((rc = ensure(ctx, ctx->d_tile_lb, (max_tiles + 1) * 4, false))) return rc;
+    const uint64_t n_tiles64 = (n_bases + P.tile - 1) / P.tile;
+    if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
     const int max_grid = ctx->sm_count * 3;
+    if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tile_base, ((uint64_t)n_tiles + 1) * 16, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_hscr, (size_t)max_grid * WIN * 4, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_status, std::max<uint64_t>(max_tiles, (n_seqs + RT * RPT - 1) / (RT * RPT)) * 8 + 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_status, ((n_seqs + RT * RPT - 1) / (RT * RPT)) * 8 + 8, false))) return rc;
 
     // capacity of the minimizer stream: expected 2*density*(kept bases), with head room; grown and rerun on overflow
     uint64_t cap;
@@ -274,56 +275,59 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         cap = std::min<uint64_t>(n_bases, (uint64_t)((double)n_bases * rate) + 65536);
     }
 
+    K1Args A;
+    A.bases = d_bases; A.seq_off = d_seq_off;
+    A.tile_lb = ptr<uint32_t>(ctx->d_tile_lb);
+    A.ticket = reinterpret_cast<uint32_t *>(small + 4);
+    A.cursor = reinterpret_cast<unsigned long long *>(small + 0);
+    A.tile_info = ptr<uint4>(ctx->d_tile_info);
+    A.min_off = ptr<uint64_t>(ctx->d_min_off);
+    A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+    A.hscr = ptr<uint32_t>(ctx->d_hscr);
+    A.err = reinterpret_cast<uint32_t *>(small + 5);
+    A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
+    A.tile = P.tile; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
+    std::memcpy(A.cls_lut, P.lut, 256);
+    std::memcpy(A.xy, P.xy, sizeof(P.xy));
+    S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, n_bases, P.tile, n_tiles,
+               ptr<uint32_t>(ctx->d_tile_lb));
+    ctx->launches += 1;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if ((rc = ensure(ctx, ctx->d_mins, cap * sizeof(uint4), false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_tmp, cap * sizeof(uint4), false))) return rc;
+        A.min_out = ptr<uint4>(ctx->d_tmp); A.min_cap = cap;
         CU(cudaMemsetAsync(small, 0, 64, st));
-        for (uint64_t s = 0; s < n_slabs; ++s) {
-            K1Args A;
-            A.bases = d_bases; A.seq_off = d_seq_off;
-            A.tile_lb = ptr<uint32_t>(ctx->d_tile_lb);
-            A.status = ptr<uint64_t>(ctx->d_status);
-            A.ticket = reinterpret_cast<uint32_t *>(small + 4);
-            A.carry_in = small + ((s & 1) ? 2 : 0);
-            A.carry_out = small + ((s & 1) ? 0 : 2);
-            A.min_out = ptr<uint4>(ctx->d_mins); A.min_cap = cap;
-            A.min_off = ptr<uint64_t>(ctx->d_min_off);
-            A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
-            A.err = reinterpret_cast<uint32_t *>(small + 5);
-            A.hscr = ptr<uint32_t>(ctx->d_hscr);
-            A.n_seqs = n_seqs; A.n_bases = n_bases;
-            A.slab_begin = s * slab_len; A.slab_end = std::min(n_bases, (s + 1) * slab_len);
-            A.n_tiles = (uint32_t)((A.slab_end - A.slab_begin + P.tile - 1) / P.tile);
-            A.tile = P.tile; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
-            std::memcpy(A.cls_lut, P.lut, 256);
-            std::memcpy(A.xy, P.xy, sizeof(P.xy));
-
-            CU(cudaMemsetAsync(A.status, 0, (uint64_t)A.n_tiles * 8, st));
-            CU(cudaMemsetAsync(A.ticket, 0, 4, st));
-            S2K_LAUNCH(k_tile_bounds, (A.n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, A.slab_begin,
-                       A.slab_end, P.tile, A.n_tiles, ptr<uint32_t>(ctx->d_tile_lb));
-            const int grid = (int)std::min<uint64_t>(A.n_tiles, (uint64_t)max_grid);
-            const size_t smem = sizeof(Smem);
-            Timing &T = ctx->tm;
-            const bool rec = T.enabled && T.n < 64;
-            if (rec) cudaEventRecord(T.ev[T.n][0], st);
-            void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
-                                              : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
-            S2K_LAUNCH(kfn, grid, NT, smem, st, true, A);
-            if (rec) { cudaEventRecord(T.ev[T.n][1], st); ++T.n; }
-            ctx->launches += 2;
-            CU(cudaGetLastError());
-        }
-        // totals -> host
-        const uint64_t *carry_final = small + ((n_slabs & 1) ? 2 : 0);
-        CU(cudaMemcpyAsync(hsmall, carry_final, 16, cudaMemcpyDeviceToHost, st));
+        const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
+        const size_t smem = sizeof(Smem);
+        Timing &T = ctx->tm;
+        const bool rec = T.enabled && T.n < 64;
+        if (rec) cudaEventRecord(T.ev[T.n][0], st);
+        void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
+                                          : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
+        S2K_LAUNCH(kfn, grid, NT, smem, st, true, A);
+        if (rec) { cudaEventRecord(T.ev[T.n][1], st); ++T.n; }
+        CU(cudaGetLastError());
+        S2K_LAUNCH(k_tile_scan, 1, ST, 0, st, false, ptr<uint4>(ctx->d_tile_info), n_tiles, ptr<ulonglong2>(ctx->d_tile_base));
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        CU(cudaMemcpyAsync(hsmall, ptr<ulonglong2>(ctx->d_tile_base) + n_tiles, 16, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         n_min = hsmall[0];
-        const uint32_t err = (uint32_t)hsmall[2];
-        if (err & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "tile look-back timed out");
         if (n_min <= cap) break;
         if (attempt == 1) return fail(ctx, S2K_ERR_INTERNAL, "minimizer capacity overflow after regrow");
         cap = n_min;                                   // exact size known now: rerun once
+    }
+    if ((rc = ensure(ctx, ctx->d_mins, std::max<uint64_t>(n_min, 1) * sizeof(uint4), false))) return rc;
+    {
+        KFArgs F;
+        F.tile_info = ptr<uint4>(ctx->d_tile_info); F.tile_base = ptr<ulonglong2>(ctx->d_tile_base);
+        F.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
+        F.min_off = ptr<uint64_t>(ctx->d_min_off); F.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+        F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = cap; F.n_tiles = n_tiles; F.tile = P.tile;
+        const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 8);
+        S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
+        CU(cudaGetLastError());
+        ctx->launches += 1;
     }
     ctx->rate_hint = std::max(ctx->rate_hint, (double)n_min / (double)n_bases);
 
@@ -460,7 +464,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     Buf *all[] = {&ctx->d_bases, &ctx->d_seq_off, &ctx->d_tile_lb, &ctx->d_status, &ctx->d_small, &ctx->d_mins,
                   &ctx->d_min_off, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
-                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
+                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos};
     for (Buf *b : all) release(*b);
@@ -633,7 +637,7 @@ int s2k_encode_rle(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, 
     CU(cudaMemsetAsync(small, 0, 64, st));
     CU(cudaMemsetAsync(ctx->d_status.p, 0, (uint64_t)n_tiles * 8, st));
     S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, ptr<uint64_t>(ctx->d_seq_off), n_seqs,
-               (uint64_t)0, n_bases, (uint32_t)RLE_TILE, n_tiles, ptr<uint32_t>(ctx->d_tile_lb));
+               n_bases, (uint32_t)RLE_TILE, n_tiles, ptr<uint32_t>(ctx->d_tile_lb));
     K4Args A;
     A.bases = ptr<uint8_t>(ctx->d_bases); A.seq_off = ptr<uint64_t>(ctx->d_seq_off);
     A.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;

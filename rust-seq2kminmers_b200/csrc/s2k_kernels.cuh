@@ -60,17 +60,16 @@ struct K1Args {
     const uint8_t  *bases;
     const uint64_t *seq_off;     // n_seqs + 1
     const uint32_t *tile_lb;     // n_tiles + 1: first i with seq_off[i] >= tile start
-    uint64_t *status;            // n_tiles, zeroed before launch
     uint32_t *ticket;            // zeroed before launch
-    const uint64_t *carry_in;    // [2] minimizers / kept bases before this slab
-    uint64_t *carry_out;         // [2]
-    uint4    *min_out;           // minimizer records (hash, start, end, seq)
+    unsigned long long *cursor;  // zeroed before launch: bump allocator over min_out
+    uint4    *tile_info;         // n_tiles: (hits, kept bases, first record lo, hi)
+    uint4    *min_out;           // minimizer records (hash, start, end, seq), grouped by tile, tiles in any order
     uint64_t  min_cap;
-    uint64_t *min_off;           // n_seqs + 1
-    uint64_t *hpc_off;           // n_seqs + 1 or null
+    uint64_t *min_off;           // n_seqs + 1: minimizers of the tile before the sequence start (tile-local)
+    uint64_t *hpc_off;           // n_seqs + 1 or null: kept bases of the tile before the sequence start
     uint32_t *hscr;              // gridDim.x * WIN words: per-CTA stash of selected hashes (stays in L2)
     uint32_t *err;
-    uint64_t  n_seqs, n_bases, slab_begin, slab_end;
+    uint64_t  n_seqs, n_bases;
     uint32_t  n_tiles, tile, halo;
     uint32_t  l, d, need, thr;
     uint8_t   cls_lut[256];      // raw byte -> 8 * base class (classes 0..5)
@@ -88,12 +87,13 @@ struct Smem {
     uint32_t f1[FW];                         // owner-space bitmap: kept bases that start a sequence
     uint32_t f2[FW];                         // ... of sequences with len <= l
     uint32_t ctxpos[XB];                     // walk-back context: distance below W0
+    uint16_t qmap[(XB + WIN) / 64 + 2];      // chunk holding kept base 64*m (coarse inverse of qoff)
     uint2    xy[64];
     uint16_t hl[HL];
     uint8_t  lut[256];
     uint32_t wsum[8];
-    uint32_t tile_id, hk, min_ex, kept_ex;
-    unsigned long long s0;
+    uint32_t tile_id, hk;
+    unsigned long long s0, rec0;
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -175,27 +175,27 @@ __device__ __forceinline__ uint2 xy_at(const Smem &S, uint32_t out8, uint32_t in
     return *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(S.xy) + (out8 << 3) + in8);
 }
 
-// Original-space position (global index into `bases`) of the kept base with window index q
-// (q < 0: context gathered by the walk-back).
-__device__ __forceinline__ int64_t pos_of(const Smem &S, int64_t W0, int q)
+// Chunk (32 raw bases) that holds the kept base with window index q >= 0.
+__device__ __forceinline__ int chunk_of(const Smem &S, int q)
 {
-    if (q < 0) return W0 - (int64_t)S.ctxpos[-1 - q];
-    int lo = 0, hi = NCHUNK;                // qoff[lo] <= q < qoff[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)S.qoff[mid] <= q) lo = mid; else hi = mid;
-    }
-    return W0 + 32 * lo + nth_set_bit(S.keepw[lo], q - (int)S.qoff[lo]);
+    int c = S.qmap[q >> 6];
+    while ((int)S.qoff[c + 1] <= q) ++c;
+    return c;
+}
+// Original-space position (global index into `bases`) of kept base q that lies in chunk c.
+__device__ __forceinline__ int64_t pos_in_chunk(const Smem &S, int64_t W0, int c, int q)
+{
+    return W0 + 32 * c + nth_set_bit(S.keepw[c], q - (int)S.qoff[c]);
 }
 
 // ------------------------------------------------------------------------------------------------ tile bounds
-__global__ void k_tile_bounds(const uint64_t *__restrict__ seq_off, uint64_t n_seqs, uint64_t slab_begin,
-                              uint64_t slab_end, uint32_t tile, uint32_t n_tiles, uint32_t *__restrict__ tile_lb)
+__global__ void k_tile_bounds(const uint64_t *__restrict__ seq_off, uint64_t n_seqs, uint64_t n_bases, uint32_t tile,
+                              uint32_t n_tiles, uint32_t *__restrict__ tile_lb)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
-    uint64_t pos = slab_begin + (uint64_t)t * tile;
-    if (pos > slab_end) pos = slab_end;
+    uint64_t pos = (uint64_t)t * tile;
+    if (pos > n_bases) pos = n_bases;
     uint64_t lo = 0, hi = n_seqs + 1;       // first i in [0, n_seqs] with seq_off[i] >= pos
     while (lo < hi) {
         uint64_t mid = lo + ((hi - lo) >> 1);
@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         const uint32_t t = S.tile_id;
         if (t >= A.n_tiles) break;
 
-        const int64_t T0 = (int64_t)(A.slab_begin + (uint64_t)t * A.tile);
-        const int64_t T1 = min(T0 + (int64_t)A.tile, (int64_t)A.slab_end);
+        const int64_t T0 = (int64_t)((uint64_t)t * A.tile);
+        const int64_t T1 = min(T0 + (int64_t)A.tile, (int64_t)A.n_bases);
         const int64_t W0 = T0 - (int64_t)A.halo;
         const bool last_tile = (uint64_t)T1 == A.n_bases;
         const uint32_t lb = A.tile_lb[t];
@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         S.qoff[2 * tid] = q; S.qoff[2 * tid + 1] = q + clo;
         if (tid == NT - 1) { S.qoff[NCHUNK] = wk; S.keepw[NCHUNK] = 0; }
         if (tid == (int)(A.halo >> 6)) S.hk = ((A.halo >> 5) & 1u) ? q + clo : q;
+        for (uint32_t m = (q + 63u) & ~63u; m < q + clo + __popc(khi); m += 64)
+            S.qmap[m >> 6] = (uint16_t)(m < q + clo ? 2 * tid : 2 * tid + 1);
 
         // ---- S4: compaction (predicated byte stores in HPC order)
         {
@@ -387,7 +389,13 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         for (int pass = 0; pass < 2; ++pass) {
             unsigned long long mask = 0ull;
             const int v0 = pass * CAP + CH * tid;
-            if ((uint32_t)(pass * CAP) < n_own) {          // uniform
+            if ((uint32_t)(pass * CAP) >= n_own) {         // uniform: nothing left for this pass
+                S.hitw[pass][tid] = 0ull;
+                S.hitpre[pass][tid] = tile_min;
+                if (tid == NT - 1) { S.hitw[pass][NT] = 0ull; S.hitpre[pass][NT] = tile_min; }
+                continue;
+            }
+            {
                 if ((uint32_t)v0 < n_own) {
                     const int n_u = min(CH, (int)n_own - v0);
                     // owners invalidated by sequence starts: a start f kills owners [f, f+l-2+d] (+1 if len<=l)
@@ -439,43 +447,15 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
             if (tid == NT - 1) { S.hitw[pass][NT] = 0ull; S.hitpre[pass][NT] = tile_min; }
         }
 
-        // ---- S6b: decoupled look-back across tiles
-        if (warp == 0) {
-            const uint64_t agg = ((uint64_t)n_own << 31) | (uint64_t)tile_min;
-            uint64_t excl = 0;
-            if (t > 0) {
-                if (lane == 0) st_relaxed(&A.status[t], FLAG_AGG | agg);
-                int64_t j = (int64_t)t - 1;
-                for (;;) {
-                    const int64_t idx = j - lane;
-                    uint64_t s = FLAG_INCL;                // tiles before the slab: inclusive prefix 0
-                    if (idx >= 0) {
-                        uint32_t spins = 0;
-                        while (((s = ld_relaxed(&A.status[idx])) >> 62) == 0) {
-                            if (++spins > SPIN_LIMIT) { atomicOr(A.err, ERR_SPIN); s = FLAG_INCL; break; }
-                            __nanosleep(40);
-                        }
-                    }
-                    const uint32_t im = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-                    const int first = im ? (__ffs(im) - 1) : 32;
-                    excl += warp_sum64(lane <= first ? (s & VALMASK) : 0ull);
-                    if (im) break;
-                    j -= 32;
-                }
-            }
-            if (lane == 0) {
-                st_relaxed(&A.status[t], FLAG_INCL | (excl + agg));
-                S.min_ex = (uint32_t)(excl & 0x7fffffffu);
-                S.kept_ex = (uint32_t)((excl >> 31) & 0x7fffffffu);
-                if (t == A.n_tiles - 1) {
-                    A.carry_out[0] = A.carry_in[0] + (excl & 0x7fffffffu) + tile_min;
-                    A.carry_out[1] = A.carry_in[1] + ((excl >> 31) & 0x7fffffffu) + n_own;
-                }
-            }
+        // ---- S6b: claim a contiguous run of records for this tile (tiles land in any order; k_finalize sorts them out)
+        if (tid == 0) {
+            const unsigned long long r0 = tile_min ? atomicAdd(A.cursor, (unsigned long long)tile_min) : 0ull;
+            S.rec0 = r0;
+            A.tile_info[t] = make_uint4(tile_min, n_own, (uint32_t)r0, (uint32_t)(r0 >> 32));
+            if (r0 + tile_min > A.min_cap) atomicOr(A.err, ERR_CAP);
         }
         __syncthreads();
-        const uint64_t min_base = A.carry_in[0] + S.min_ex;
-        const uint64_t kept_base = A.carry_in[1] + S.kept_ex;
+        const uint64_t rec0 = S.rec0;
 
         // ---- S7: ordered hit list in shared memory, then one thread per minimizer
         for (uint32_t base = 0; base < tile_min; base += HL) {
@@ -497,8 +477,12 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
                 const int v = S.hl[j];
                 const int qo = (int)hk + v;                // window index of the owner base
                 const uint32_t h = hs[v];
-                const int64_t g_own = pos_of(S, W0, qo);
-                const int64_t g_start = pos_of(S, W0, qo - (l - 1 + d));
+                int c = chunk_of(S, qo);
+                const int64_t g_own = pos_in_chunk(S, W0, c, qo);
+                const int qs = qo - (l - 1 + d);           // first base of the l-mer: a little further left
+                int64_t g_start;
+                if (qs < 0) g_start = W0 - (int64_t)S.ctxpos[-1 - qs];
+                else { while ((int)S.qoff[c] > qs) --c; g_start = pos_in_chunk(S, W0, c, qs); }
                 uint32_t lo = lb, hi = ub;                 // first i in [lb,ub) with seq_off[i] > g_own
                 while (lo < hi) {
                     const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -506,12 +490,10 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
                 }
                 const uint32_t rid = lo - 1;
                 const uint64_t so = A.seq_off[rid];
-                const uint64_t idx = min_base + base + j;
+                const uint64_t idx = rec0 + base + j;
                 if (idx < A.min_cap)
                     A.min_out[idx] = make_uint4(h, (uint32_t)((uint64_t)g_start - so),
                                                 (uint32_t)((uint64_t)g_own - (uint64_t)d - so), rid);
-                else
-                    atomicOr(A.err, ERR_CAP);
             }
         }
         // ---- S8: per-sequence offsets for every sequence starting in this tile
@@ -523,8 +505,69 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
             const uint32_t pass = v >= (uint32_t)CAP ? 1u : 0u;
             const uint32_t vv = v - pass * CAP, u = vv / CH, bit = vv - u * CH;
             const uint32_t hb = S.hitpre[pass][u] + __popcll(S.hitw[pass][u] & lowmask64(bit));
-            A.min_off[i] = min_base + hb;
-            if (A.hpc_off) A.hpc_off[i] = kept_base + v;
+            A.min_off[i] = hb;
+            if (A.hpc_off) A.hpc_off[i] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tile order
+// Exclusive prefix over tiles of (hits, kept bases): one CTA, each thread owns a contiguous run of tiles.
+constexpr int ST = 1024;
+__global__ void __launch_bounds__(ST) k_tile_scan(const uint4 *__restrict__ tile_info, uint32_t n_tiles,
+                                                  ulonglong2 *__restrict__ tile_base)
+{
+    S2K_SHARED unsigned long long sm[ST], sk[ST];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (n_tiles + ST - 1) / ST;
+    const uint32_t b = min(tid * per, n_tiles), e = min(b + per, n_tiles);
+    unsigned long long m = 0, k = 0;
+    for (uint32_t t = b; t < e; ++t) { const uint4 x = tile_info[t]; m += x.x; k += x.y; }
+    sm[tid] = m; sk[tid] = k;
+    __syncthreads();
+    for (uint32_t o = 1; o < ST; o <<= 1) {
+        unsigned long long am = 0, ak = 0;
+        if (tid >= o) { am = sm[tid - o]; ak = sk[tid - o]; }
+        __syncthreads();
+        sm[tid] += am; sk[tid] += ak;
+        __syncthreads();
+    }
+    unsigned long long pm = sm[tid] - m, pk = sk[tid] - k;
+    for (uint32_t t = b; t < e; ++t) {
+        const uint4 x = tile_info[t];
+        tile_base[t] = make_ulonglong2(pm, pk);
+        pm += x.x; pk += x.y;
+    }
+    if (tid == ST - 1) tile_base[n_tiles] = make_ulonglong2(sm[ST - 1], sk[ST - 1]);
+}
+
+// One warp per tile: move the tile's records to their final, ordered place and turn the tile-local
+// per-sequence offsets into global ones.
+struct KFArgs {
+    const uint4 *tile_info;
+    const ulonglong2 *tile_base;
+    const uint32_t *tile_lb;
+    const uint4 *tmp;
+    uint4 *mins;
+    uint64_t *min_off, *hpc_off;
+    uint64_t n_seqs, n_bases, min_cap;
+    uint32_t n_tiles, tile;
+};
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs A)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < A.n_tiles; t += nwarps) {
+        const uint4 info = A.tile_info[t];
+        const ulonglong2 base = A.tile_base[t];
+        const uint64_t src = ((uint64_t)info.w << 32) | info.z;
+        if (src + info.x <= A.min_cap)
+            for (uint32_t j = lane; j < info.x; j += 32) A.mins[base.x + j] = A.tmp[src + j];
+        const bool last_tile = (uint64_t)(t + 1) * A.tile >= A.n_bases;
+        const uint32_t lb = A.tile_lb[t], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
+        for (uint32_t i = lb + lane; i < ub; i += 32) {
+            A.min_off[i] += base.x;
+            if (A.hpc_off) A.hpc_off[i] += base.y;
         }
     }
 }

@@ -30,6 +30,8 @@ struct uint2 { uint32_t x, y; };
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 
 namespace emu {
@@ -145,6 +147,7 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s)
 static inline void __nanosleep(unsigned) { sched_yield(); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
 template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
