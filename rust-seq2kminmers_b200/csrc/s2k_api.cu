@@ -259,7 +259,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     const uint64_t n_tiles64 = (n_bases + P.tile - 1) / P.tile;
     if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
     const uint32_t n_tiles = (uint32_t)n_tiles64;
-    const int max_grid = ctx->sm_count * 3;
+    const int max_grid = ctx->sm_count * S2K_MINB;
     if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_tile_base, ((uint64_t)n_tiles + 1) * 16, false))) return rc;

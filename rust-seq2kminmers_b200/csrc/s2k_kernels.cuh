@@ -41,12 +41,14 @@ constexpr int NT    = 256;          // threads per CTA
 constexpr int RAWPT = 64;           // raw bases per thread in the keep/compaction phase
 constexpr int WIN   = NT * RAWPT;   // raw bases staged per tile (left halo + tile)
 constexpr int NCHUNK = WIN / 32;    // 32-base chunks per window
-constexpr int CH    = 60;           // owner positions per thread in the hash phase: 15 words, an odd word stride,
-                                    // so the per-lane byte streams of a warp fall into 32 different banks
+constexpr int CH    = 52;           // owner positions per thread in the hash phase: 13 words, an odd word stride,
+                                    // so the per-lane byte streams of a warp fall into 32 different banks; with
+                                    // ~75 % of bases kept, 256 x 52 owners just cover a 16 128-base HPC tile
 constexpr int CAP   = NT * CH;      // owners hashed per pass (a second pass covers tiles that compress badly)
 constexpr int XB    = 256;          // capacity of the left context, in kept (HPC) bases
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
 constexpr int HL    = 1024;         // hit-list entries emitted per round
+constexpr int DIRTY_MAX = 62;
 constexpr int ZC8   = 4 * 8;        // pre-scaled base class whose forward and reverse seeds are both 0
 
 constexpr uint64_t FLAG_AGG  = 1ull << 62;
@@ -93,6 +95,8 @@ struct Smem {
     uint8_t  lut[256];
     uint32_t wsum[8];
     uint32_t tile_id, hk;
+    uint32_t n_dirty[2];                     // flag words set during this tile (cleared at the next loop top);
+    uint16_t dirty[2][DIRTY_MAX];            // double-buffered by tile parity.  bit 15: f1/f2, else startw/shortw
     unsigned long long s0, rec0;
 };
 
@@ -170,6 +174,22 @@ template <bool W31> __device__ __forceinline__ uint32_t ror1(uint32_t x)
     if (W31) return (x >> 1) | ((x & 1u) << 30);
     return __funnelshift_r(x, x, 1);
 }
+// Sequence-start flags are sparse: remember which bitmap words were touched so that the next tile clears those
+// instead of zeroing four bitmaps.  More than DIRTY_MAX touched words -> the next tile zeroes everything.
+__device__ __forceinline__ void flag_raw(Smem &S, int par, uint32_t x, bool is_short)
+{
+    atomicOr(&S.startw[x >> 5], 1u << (x & 31));
+    if (is_short) atomicOr(&S.shortw[x >> 5], 1u << (x & 31));
+    const uint32_t k = atomicAdd(&S.n_dirty[par], 1u);
+    if (k < DIRTY_MAX) S.dirty[par][k] = (uint16_t)(x >> 5);
+}
+__device__ __forceinline__ void flag_owner(Smem &S, int par, int oo, bool is_short)
+{
+    atomicOr(&S.f1[oo >> 5], 1u << (oo & 31));
+    if (is_short) atomicOr(&S.f2[oo >> 5], 1u << (oo & 31));
+    const uint32_t k = atomicAdd(&S.n_dirty[par], 1u);
+    if (k < DIRTY_MAX) S.dirty[par][k] = (uint16_t)(0x8000u | (uint32_t)(oo >> 5));
+}
 __device__ __forceinline__ uint2 xy_at(const Smem &S, uint32_t out8, uint32_t in8)
 {
     return *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(S.xy) + (out8 << 3) + in8);
@@ -218,8 +238,11 @@ __global__ void k_tile_bounds(const uint64_t *__restrict__ seq_off, uint64_t n_s
 //   S7  hits are listed in order in shared memory and handed out one per thread: positions by rank/select on
 //       the keep masks, sequence index by binary search of seq_off, one 16-byte record store per minimizer
 //   S8  per-sequence offsets (minimizers, kept bases) for every sequence that starts in the tile
+#ifndef S2K_MINB
+#define S2K_MINB 3                  // CTAs per SM the minimizer kernel is compiled for (register cap)
+#endif
 template <bool HPC, bool W31>
-__global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1Args A)
+__global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_constant__ K1Args A)
 {
     S2K_DYN_SMEM(smem_raw);
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -230,13 +253,28 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
     for (int i = tid; i < 256; i += NT) S.lut[i] = A.cls_lut[i];
     if (tid < 64) S.xy[tid] = A.xy[tid];
     for (int i = tid; i < XB + WIN + 128; i += NT) S.code[i] = ZC8;
+    for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
+    for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
+    if (tid == 0) { S.n_dirty[0] = 0; S.n_dirty[1] = 0; }
+    int par = 1;                                           // parity of the tile being processed
 
     for (;;) {
         __syncthreads();                                   // everyone is done with the previous tile
         if (tid == 0) S.tile_id = atomicAdd(A.ticket, 1u);
-        for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
-        for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
+        {   // clear the flag words the previous tile (parity `par`) touched
+            const uint32_t nd = S.n_dirty[par];
+            if (nd > DIRTY_MAX) {
+                for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
+                for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
+            } else if ((uint32_t)tid < nd) {
+                const uint32_t e = S.dirty[par][tid];
+                if (e & 0x8000u) { S.f1[e & 0x7fffu] = 0; S.f2[e & 0x7fffu] = 0; }
+                else { S.startw[e] = 0; S.shortw[e] = 0; }
+            }
+        }
         __syncthreads();
+        if (tid == 0) S.n_dirty[par] = 0;                  // consumed; reused by the tile after this one
+        par ^= 1;
         const uint32_t t = S.tile_id;
         if (t >= A.n_tiles) break;
 
@@ -273,10 +311,8 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
         for (uint32_t i = lb + tid; i < ub; i += NT) {
             const uint64_t so = A.seq_off[i];
             if (so < (uint64_t)T1) {
-                const uint32_t x = (uint32_t)((int64_t)so - W0);
-                atomicOr(&S.startw[x >> 5], 1u << (x & 31));
                 const uint64_t len = A.seq_off[i + 1] - so;
-                if (len > 0 && len <= (uint64_t)l) atomicOr(&S.shortw[x >> 5], 1u << (x & 31));
+                flag_raw(S, par, (uint32_t)((int64_t)so - W0), len > 0 && len <= (uint64_t)l);
             }
         }
         if (tid == 0) {
@@ -285,9 +321,7 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
             if (so_lb != (uint64_t)T0) {                   // the sequence containing T0 started earlier
                 s0 = A.seq_off[lb - 1];
                 if ((int64_t)s0 >= W0) {
-                    const uint32_t x = (uint32_t)((int64_t)s0 - W0);
-                    atomicOr(&S.startw[x >> 5], 1u << (x & 31));
-                    if (so_lb - s0 <= (uint64_t)l) atomicOr(&S.shortw[x >> 5], 1u << (x & 31));
+                    flag_raw(S, par, (uint32_t)((int64_t)s0 - W0), so_lb - s0 <= (uint64_t)l);
                 }
             }
             S.s0 = s0;
@@ -348,10 +382,7 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
                 const int b = __ffsll((long long)sw) - 1;
                 sw &= sw - 1;
                 const int oo = (int)q + __popcll(keep & lowmask64(b)) - (int)hk + XB;
-                if (oo >= 0) {
-                    atomicOr(&S.f1[oo >> 5], 1u << (oo & 31));
-                    if ((sh2 >> b) & 1ull) atomicOr(&S.f2[oo >> 5], 1u << (oo & 31));
-                }
+                if (oo >= 0) flag_owner(S, par, oo, (sh2 >> b) & 1ull);
             }
         }
         // ---- S4b: not enough context in the halo -> walk back through the sequence (rare: long homopolymers)
@@ -374,7 +405,7 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
                     const uint32_t slot = taken + rank;            // 0 = nearest to the window
                     S.code[XB - 1 - (int)slot] = S.lut[b];
                     S.ctxpos[slot] = (uint32_t)(W0 - g);
-                    if (g == s0) { const int oo = XB - 1 - (int)slot - (int)hk; if (oo >= 0) atomicOr(&S.f1[oo >> 5], 1u << (oo & 31)); }
+                    if (g == s0) { const int oo = XB - 1 - (int)slot - (int)hk; if (oo >= 0) flag_owner(S, par, oo, false); }
                 }
                 const uint32_t c = min((uint32_t)__popc(m), remaining);
                 taken += c; remaining -= c; hi = lo;
@@ -426,17 +457,27 @@ __global__ void __launch_bounds__(NT, 3) k_minimizers(const __grid_constant__ K1
                         rh = ror1<W31>(rh) ^ tt.y;
                     }
                     const uint8_t *co = cb - l;
+                    static_assert(CH % 4 == 0, "hits are tested once per group of four owners");
 #pragma unroll
-                    for (int i = 0; i < CH; ++i) {
-                        const uint32_t in8 = cb[i];
-                        const uint32_t out8 = i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8;
-                        const uint2 tt = xy_at(S, out8, in8);
-                        fh = rol1<W31>(fh) ^ tt.x;
-                        rh = ror1<W31>(rh) ^ tt.y;
-                        const uint32_t h = min(fh, rh);
-                        if (h <= A.thr && i < n_u) { mask |= 1ull << i; hs[v0 + i] = h; }
+                    for (int i0 = 0; i0 < CH; i0 += 4) {
+                        uint32_t hv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = i0 + k;
+                            const uint32_t in8 = cb[i];
+                            const uint32_t out8 = i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8;
+                            const uint2 tt = xy_at(S, out8, in8);
+                            fh = rol1<W31>(fh) ^ tt.x;
+                            rh = ror1<W31>(rh) ^ tt.y;
+                            hv[k] = min(fh, rh);
+                        }
+                        if (min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= A.thr) {   // rare: ~8 % of groups at d=0.01
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (hv[k] <= A.thr) { mask |= 1ull << (i0 + k); hs[v0 + i0 + k] = hv[k]; }
+                        }
                     }
-                    mask &= ~invalid;
+                    mask &= ~invalid & lowmask64((uint32_t)n_u);     // owners >= n_u hashed garbage
                 }
             }
             uint32_t tot;
