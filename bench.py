@@ -210,9 +210,12 @@ def main():
     value = world * n_bases / (ms_step * 1e-3) / 1e9
 
     # optional final gather of per-GPU counts over NCCL (the only collective; not on the data path)
-    counts = torch.tensor([n_items, n_min], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        sharding = importlib.import_module("rust-seq2kminmers_b200.sharding")
+        per_rank, _first_item = sharding.gather_totals(n_items, n_min, device=dev)
+        counts = torch.tensor(per_rank.sum(axis=0))
+    else:
+        counts = torch.tensor([n_items, n_min], dtype=torch.int64)
 
     # roofline of the dominant kernel (k_minimizers): algorithmic bytes = bases + offsets + 17 B per item
     alg_bytes = n_bases + 8 * (n_reads + 1) + 17 * n_items

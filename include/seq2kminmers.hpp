@@ -1,0 +1,107 @@
+// seq2kminmers.hpp -- header-only C++ host side above the C ABI (seq2kminmers.h).
+//
+// The reference is a Rust crate; this image has no Rust toolchain, so the host-side mirror of its operator API
+// is written in C++ (the Rust binding a maintainer would add is shown in INTEGRATION.md).  Names, argument
+// order and error behaviour follow the reference:
+//   HashMode                         src/lib.rs:21-27
+//   KminmerHash{hash,start,end,offset,rev}, equality/order on .hash only     src/kminmer.rs:128-135,181-203
+//   KminmersIterator::new(seq,l,k,density,mode) -> iterator of KminmerHash   src/lib.rs:89,179-270
+//   encode_rle_simd / hpc                                                    src/hpc.rs:28-41,44-147
+// Where the reference panics (unwrap/assert) this wrapper throws s2k::Error carrying the C status code.
+#pragma once
+#include "seq2kminmers.h"
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace s2k {
+
+enum class HashMode : int { Regular = 0, Hpc = 1, Simd = 2, HpcSimd = 3 };
+enum class HashVariant : int { NT1_32 = 0, NT2_31 = 1 };
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int st, const std::string &m) : std::runtime_error("s2k status " + std::to_string(st) + ": " + m), status(st) {}
+};
+
+struct KminmerHash {
+    uint64_t hash;
+    size_t start, end, offset;
+    bool rev;
+    uint64_t get_hash() const { return hash; }                                     // trait Kminmer
+    bool operator==(const KminmerHash &o) const { return hash == o.hash; }         // src/kminmer.rs:181-185
+    bool operator<(const KminmerHash &o) const { return hash < o.hash; }           // src/kminmer.rs:193-197
+};
+using KminmerType = KminmerHash;
+
+// One CUDA device + stream + buffers; single-threaded like one iterator (src/main.rs:65-79).
+class Context {
+  public:
+    explicit Context(int device = 0)
+    {
+        int st = s2k_ctx_create(device, &ctx_);
+        if (st != S2K_OK) throw Error(st, std::string(s2k_strerror(st)) + " (no CUDA device? there is no CPU fallback)");
+    }
+    ~Context() { s2k_ctx_destroy(ctx_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+
+    // Batched KminmersIterator::new + collect.  Result pointers stay valid until the next run on this context.
+    s2k_result run(const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, size_t l, size_t k, double density,
+                   HashMode mode, HashVariant variant = HashVariant::NT1_32)
+    {
+        s2k_params p{(uint32_t)l, (uint32_t)k, density, (int32_t)mode, (int32_t)variant};
+        s2k_result r;
+        check(s2k_run(ctx_, bases, seq_off, n_seqs, &p, &r));
+        return r;
+    }
+    s2k_rle_result encode_rle(const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs)
+    {
+        s2k_rle_result r;
+        check(s2k_encode_rle(ctx_, bases, seq_off, n_seqs, &r));
+        return r;
+    }
+    s2k_ctx *raw() { return ctx_; }
+
+  private:
+    void check(int st)
+    {
+        if (st != S2K_OK) throw Error(st, s2k_last_error(ctx_));
+    }
+    s2k_ctx *ctx_ = nullptr;
+};
+
+// KminmersIterator::new(seq, l, k, density, mode): the sequence is processed on the GPU at construction (a batch
+// of one); begin()/end() then walk the items in the reference's order.  For throughput use Context::run.
+class KminmersIterator {
+  public:
+    KminmersIterator(Context &ctx, const uint8_t *seq, size_t len, size_t l, size_t k, double density, HashMode mode,
+                     HashVariant variant = HashVariant::NT1_32)
+    {
+        const uint64_t off[2] = {0, len};
+        const s2k_result r = ctx.run(seq, off, 1, l, k, density, mode, variant);
+        items_.reserve(r.n_items);
+        for (uint64_t i = 0; i < r.n_items; ++i)
+            items_.push_back(KminmerHash{r.hash[i], r.start[i], r.end[i], (size_t)i, r.rev[i] != 0});
+    }
+    std::vector<KminmerHash>::const_iterator begin() const { return items_.begin(); }
+    std::vector<KminmerHash>::const_iterator end() const { return items_.end(); }
+    const std::vector<KminmerHash> &collect() const { return items_; }
+
+  private:
+    std::vector<KminmerHash> items_;
+};
+
+// encode_rle_simd(s) -> (hpc string, run-start positions)   src/hpc.rs:44
+inline std::pair<std::string, std::vector<uint32_t>> encode_rle_simd(Context &ctx, const uint8_t *seq, size_t len)
+{
+    const uint64_t off[2] = {0, len};
+    const s2k_rle_result r = ctx.encode_rle(seq, off, 1);
+    return {std::string(reinterpret_cast<const char *>(r.hpc), r.n_hpc), std::vector<uint32_t>(r.pos, r.pos + r.n_hpc)};
+}
+inline std::string hpc(Context &ctx, const uint8_t *seq, size_t len) { return encode_rle_simd(ctx, seq, len).first; }
+
+} // namespace s2k

@@ -141,8 +141,8 @@ struct Plan {
     bool hpc, simd, w31, quirk;
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
-    uint8_t lut[256];   // raw byte -> 8 * base class
-    uint2 xy[64];
+    uint8_t lut[256];   // raw byte -> code of its base class
+    uint2 xy[XYN];
 };
 
 // Validation mirrors the reference's panics: assert!(k<=31) (src/nthash_avx512_32.rs:33) for the SIMD modes,
@@ -180,17 +180,21 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         rc[b] = P.w31 ? (uint32_t)(SEED64[3 - b] >> 33) : (uint32_t)SEED64[3 - b];
     }
     h[5] = rc[5] = 1;
+    static const uint8_t code_of[6] = {0, 8, 16, 24, 128, 136};   // see s2k_kernels.cuh (table layout)
     if (P.simd) {                                    // low nibble, src/nthash_avx512_32.rs:178-193
         static const uint8_t nib[16] = {4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4};
-        for (int i = 0; i < 256; ++i) P.lut[i] = (uint8_t)(8 * nib[i & 15]);
+        for (int i = 0; i < 256; ++i) P.lut[i] = code_of[nib[i & 15]];
     } else {                                         // src/nthash_hpc.rs:29-49
-        for (int i = 0; i < 256; ++i) P.lut[i] = 8 * 5;
-        P.lut['A'] = 8 * 0; P.lut['C'] = 8 * 1; P.lut['G'] = 8 * 2; P.lut['T'] = 8 * 3; P.lut['N'] = 8 * 4;
+        for (int i = 0; i < 256; ++i) P.lut[i] = code_of[5];
+        P.lut['A'] = code_of[0]; P.lut['C'] = code_of[1]; P.lut['G'] = code_of[2]; P.lut['T'] = code_of[3];
+        P.lut['N'] = code_of[4];
     }
-    for (int o = 0; o < 8; ++o)
-        for (int i = 0; i < 8; ++i) {
-            P.xy[o * 8 + i].x = rolw(h[o], P.l, w) ^ h[i];
-            P.xy[o * 8 + i].y = rorw(rc[o], 1, w) ^ rolw(rc[i], P.l - 1, w);
+    std::memset(P.xy, 0, sizeof(P.xy));
+    for (int o = 0; o < 6; ++o)
+        for (int i = 0; i < 6; ++i) {
+            const int slot = (4 * code_of[o] + code_of[i]) / 8;
+            P.xy[slot].x = rolw(h[o], P.l, w) ^ h[i];
+            P.xy[slot].y = rorw(rc[o], 1, w) ^ rolw(rc[i], P.l - 1, w);
         }
     return S2K_OK;
 }

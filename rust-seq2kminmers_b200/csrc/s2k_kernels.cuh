@@ -49,7 +49,11 @@ constexpr int XB    = 256;          // capacity of the left context, in kept (HP
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
 constexpr int HL    = 1024;         // hit-list entries emitted per round
 constexpr int DIRTY_MAX = 62;
-constexpr int ZC8   = 4 * 8;        // pre-scaled base class whose forward and reverse seeds are both 0
+// Base classes are stored pre-scaled so that one IMAD forms the table address: code(A,C,G,T) = 0,8,16,24 and
+// the two rare classes (seed 0 / seed 1) = 128,136.  Entry (out,in) lives at byte 4*code(out)+code(in): the sixteen
+// ACGT x ACGT entries fill bytes 0..127 exactly -- one bank each -- so table loads never conflict on ACGT input.
+constexpr int XYN   = 86;           // (4*136 + 136 + 8) / 8 table slots
+constexpr int ZC8   = 128;          // code of the class whose forward and reverse seeds are both 0
 
 constexpr uint64_t FLAG_AGG  = 1ull << 62;
 constexpr uint64_t FLAG_INCL = 2ull << 62;
@@ -75,7 +79,7 @@ struct K1Args {
     uint32_t  n_tiles, tile, halo;
     uint32_t  l, d, need, thr;
     uint8_t   cls_lut[256];      // raw byte -> 8 * base class (classes 0..5)
-    uint2     xy[64];            // [out*8+in] -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
+    uint2     xy[XYN];           // byte offset 4*code(out)+code(in) -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
 };
 
 struct Smem {
@@ -90,7 +94,7 @@ struct Smem {
     uint32_t f2[FW];                         // ... of sequences with len <= l
     uint32_t ctxpos[XB];                     // walk-back context: distance below W0
     uint16_t qmap[(XB + WIN) / 64 + 2];      // chunk holding kept base 64*m (coarse inverse of qoff)
-    uint2    xy[64];
+    uint2    xy[XYN];
     uint16_t hl[HL];
     uint8_t  lut[256];
     uint32_t wsum[8];
@@ -192,7 +196,7 @@ __device__ __forceinline__ void flag_owner(Smem &S, int par, int oo, bool is_sho
 }
 __device__ __forceinline__ uint2 xy_at(const Smem &S, uint32_t out8, uint32_t in8)
 {
-    return *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(S.xy) + (out8 << 3) + in8);
+    return *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(S.xy) + (out8 << 2) + in8);
 }
 
 // Chunk (32 raw bases) that holds the kept base with window index q >= 0.
@@ -239,7 +243,7 @@ __global__ void k_tile_bounds(const uint64_t *__restrict__ seq_off, uint64_t n_s
 //       the keep masks, sequence index by binary search of seq_off, one 16-byte record store per minimizer
 //   S8  per-sequence offsets (minimizers, kept bases) for every sequence that starts in the tile
 #ifndef S2K_MINB
-#define S2K_MINB 3                  // CTAs per SM the minimizer kernel is compiled for (register cap)
+#define S2K_MINB 4                  // CTAs per SM the minimizer kernel is compiled for (register cap)
 #endif
 template <bool HPC, bool W31>
 __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_constant__ K1Args A)
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     uint32_t *const hs = A.hscr + (size_t)blockIdx.x * WIN;
 
     for (int i = tid; i < 256; i += NT) S.lut[i] = A.cls_lut[i];
-    if (tid < 64) S.xy[tid] = A.xy[tid];
+    if (tid < XYN) S.xy[tid] = A.xy[tid];
     for (int i = tid; i < XB + WIN + 128; i += NT) S.code[i] = ZC8;
     for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
     for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }

@@ -143,3 +143,14 @@ def test_error_codes(S, gpu_ctx):
         with pytest.raises(S.S2KError) as e:
             gpu_ctx.run(b, so, *args)
         assert e.value.status == status
+
+
+def test_cpp_host_wrapper_twin_of_reference_test(S, tmp_path):
+    """include/seq2kminmers.hpp: the C++ twin of the reference's tests/main.rs, linked against the product library."""
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "test_main"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", str(exe), str(ROOT / "tests" / "cpp" / "test_main.cpp"),
+                    f"-L{S.PKG_DIR}", "-l:libs2k_b200.so", f"-Wl,-rpath,{S.PKG_DIR}"], check=True)
+    out = subprocess.run([str(exe), str(ROOT / "tests" / "golden" / "ecoli100k.2bit")], capture_output=True, text=True)
+    assert out.returncode == 0 and "test_main ok" in out.stdout, out.stdout + out.stderr
