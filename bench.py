@@ -88,18 +88,25 @@ def cpu_port_rate(O, L, seed, mode, variant, threads, target_s=12.0, first_read=
     probe_reads = max(threads * 4, int(2_000_000 // max(L, 1)) + 1) if L < 10_000_000 else 1
     probe_len = L if L < 10_000_000 else 20_000_000
 
+    use_avx = variant == 0 and mode in (2, 3) and O.has_avx512()
+
     def run(n_reads, read_len):
         bases = O.synth(seed, first_read * L, n_reads * read_len)
         so = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
         t0 = time.perf_counter()
-        r = O.batch(bases, so, L_PARAM, K_PARAM, DENSITY, mode, variant, threads=threads, want_counts=False)
+        if use_avx:      # AVX-512 restatement of the reference's vector path (oracle/s2k_cpu_avx512.c)
+            r = O.avx512_batch(bases, so, L_PARAM, K_PARAM, DENSITY, mode, threads=threads, want_counts=False)
+        else:            # scalar restatement (oracle/s2k_oracle.c)
+            r = O.batch(bases, so, L_PARAM, K_PARAM, DENSITY, mode, variant, threads=threads, want_counts=False)
         return time.perf_counter() - t0, n_reads * read_len, r["total"]
 
     dt, nb, _ = run(probe_reads, probe_len)
     rate = nb / dt
     n_reads = max(probe_reads, int(rate * target_s / probe_len))
     dt, nb, items = run(n_reads, probe_len)
-    return nb / dt / 1e9, dt, f"{n_reads} reads x {probe_len} bp = {nb / 1e9:.3f} Gbp of the same synthetic stream, {dt:.1f} s"
+    impl = "AVX-512 C restatement of the reference's vector path (oracle/s2k_cpu_avx512.c)" if use_avx else \
+        "scalar C restatement of the reference iterator (oracle/s2k_oracle.c)"
+    return nb / dt / 1e9, dt, f"{n_reads} reads x {probe_len} bp = {nb / 1e9:.3f} Gbp of the same synthetic stream, {dt:.1f} s; {impl}"
 
 
 def main():
@@ -149,7 +156,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": threads, "kind": "port",
-                                 "sample": "each step: " + sample + "; C restatement of the reference iterator (oracle/), "
+                                 "sample": "each step: " + sample + "; one iterator per read on all host threads (src/main.rs:65-79); "
                                            "the Rust crate itself is unbuildable here"},
                 "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -256,7 +263,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         g, dt, sample = cpu_port_rate(O, L, seed, mode, variant, threads, target_s=12.0)
         cpu = {"value": g, "unit": "Gbp/s", "cores": threads, "kind": "port",
-               "sample": sample + "; multi-threaded C restatement of the reference iterator (oracle/), one iterator per read"}
+               "sample": sample + "; one iterator per read on all host threads (src/main.rs:65-79)"}
 
     if rank == 0:
         line = {"metric": "input Gbp/s -> k-min-mers", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,

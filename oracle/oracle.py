@@ -22,8 +22,8 @@ _lib = None
 
 
 def build(force: bool = False) -> Path:
-    src = HERE / "s2k_oracle.c"
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    srcs = [HERE / "s2k_oracle.c", HERE / "s2k_cpu_avx512.c", HERE / "Makefile"]
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(HERE), "-B" if force else "-s"], check=True,
                        stdout=subprocess.DEVNULL)
     return LIB_PATH
@@ -69,6 +69,11 @@ def lib() -> C.CDLL:
         L.s2k_oracle_batch.restype = C.c_long
         L.s2k_oracle_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.s2k_cpu_has_avx512.restype = C.c_int
+        L.s2k_cpu_has_avx512.argtypes = []
+        L.s2k_cpu_avx512_batch.restype = C.c_long
+        L.s2k_cpu_avx512_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int,
+                                           C.c_int, C.c_void_p, C.c_void_p]
         L.s2k_oracle_digest_items.restype = None
         L.s2k_oracle_digest_items.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p]
         _lib = L
@@ -206,6 +211,23 @@ def batch(bases, seq_off, l, k, density, mode, variant=NT1_32, threads=1, want_c
     tot = lib().s2k_oracle_batch(_p(b), _p(so), n, l, k, density, mode, variant, threads, _p(km), _p(mc), _p(dg),
                                  C.byref(tm))
     return dict(total=int(tot), total_min=int(tm.value), km_cnt=km, min_cnt=mc, digest=dg)
+
+
+def has_avx512() -> bool:
+    return bool(lib().s2k_cpu_has_avx512())
+
+
+def avx512_batch(bases, seq_off, l, k, density, mode, threads=1, want_counts=True, want_digest=False):
+    """AVX-512 restatement of the reference's Simd/HpcSimd path (oracle/s2k_cpu_avx512.c): the CPU baseline."""
+    b = _seq(bases)                     # each read is copied into a padded per-thread buffer inside the C code
+    so = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    n = len(so) - 1
+    km = np.zeros(n, dtype=np.uint64) if want_counts else None
+    dg = np.zeros(n, dtype=np.uint64) if want_digest else None
+    tot = lib().s2k_cpu_avx512_batch(_p(b), _p(so), n, l, k, density, mode, threads, _p(km), _p(dg))
+    if tot < 0:
+        raise RuntimeError("AVX-512 baseline unavailable (CPU flags or mode)")
+    return dict(total=int(tot), km_cnt=km, digest=dg)
 
 
 def digest_items(hash_, start, end, rev, km_off) -> np.ndarray:

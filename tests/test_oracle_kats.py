@@ -143,3 +143,18 @@ def test_window_stage_rolling_equals_closed(O, batches):
         _, _, mh = O.minimizers(s, 11, 0.05, O.REGULAR)
         h, rv = O.closed_windows(mh, k)
         assert np.array_equal(h, r["hash"]) and np.array_equal(rv, r["rev"])
+
+
+def test_avx512_baseline_equals_scalar_oracle(O, batches):
+    """oracle/s2k_cpu_avx512.c (the CPU baseline bench.py reports) is bit-exact against the scalar restatement."""
+    if not O.has_avx512():
+        pytest.skip("host CPU lacks AVX-512")
+    lens = [20000] * 10 + [150] * 100 + [0, 5, 31, 32, 33, 46, 47, 48, 62, 63, 64, 50000] + list(batches.rng.integers(0, 300, 200))
+    bases, so = batches.pack([batches.seq(n, alphabet=b"ACGT" if i % 5 else b"ACGTNacgt", runp=0.3 if i % 3 == 0 else 0.0)
+                              for i, n in enumerate(lens)])
+    for mode in (O.SIMD, O.HPCSIMD):
+        for (l, k, d) in [(31, 5, 0.01), (31, 2, 0.5), (5, 3, 0.2), (16, 1, 1.0)]:
+            a = O.avx512_batch(bases, so, l, k, d, mode, threads=3, want_digest=True)
+            b = O.batch(bases, so, l, k, d, mode, 0, threads=3, want_digest=True)
+            assert a["total"] == b["total"] and np.array_equal(a["km_cnt"], b["km_cnt"])
+            assert np.array_equal(a["digest"], b["digest"]), (mode, l, k, d)
