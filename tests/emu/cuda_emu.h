@@ -144,6 +144,18 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s)
     s &= 31;
     return s ? (lo >> s) | (hi << (32 - s)) : lo;
 }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    const unsigned long long pool = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned n = (sel >> (4 * i)) & 0xf;
+        unsigned byte = (unsigned)(pool >> (8 * (n & 7))) & 0xff;
+        if (n & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
 static inline void __nanosleep(unsigned) { sched_yield(); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
