@@ -41,7 +41,6 @@ constexpr int NT    = 256;          // threads per CTA
 constexpr int RAWPT = 64;           // raw bases per thread in the keep/compaction phase
 constexpr int WIN   = NT * RAWPT;   // raw bases staged per tile (left halo + tile)
 constexpr int NCHUNK = WIN / 32;    // 32-base chunks per window
-constexpr int SEG   = WIN / 4;      // a thread handles one 16-byte piece in each of the window's four segments
 constexpr int CH    = 52;           // owner positions per thread in the hash phase: 13 words, an odd word stride,
                                     // so the per-lane byte streams of a warp fall into 32 different banks; with
                                     // ~75 % of bases kept, 256 x 52 owners just cover a 16 128-base HPC tile
@@ -84,7 +83,6 @@ struct K1Args {
 };
 
 struct Smem {
-    uint8_t  front_pad[16];                  // the warm-up may read one aligned word in front of code[]
     uint8_t  code[XB + WIN + 128];           // 8*class of every kept base, index XB + (kept index in the window)
     unsigned long long hitw[2][NT + 1];      // per pass, per thread: selected owners (bit i = owner 60*t + i)
     uint32_t hitpre[2][NT + 1];              // ... and how many hits precede that thread in the tile
@@ -99,9 +97,8 @@ struct Smem {
     uint2    xy[XYN];
     uint16_t hl[HL];
     uint8_t  lut[256];
-    unsigned long long wsum64[8];
     uint32_t wsum[8];
-    uint32_t tile_id;
+    uint32_t tile_id, hk;
     uint32_t n_dirty[2];                     // flag words set during this tile (cleared at the next loop top);
     uint16_t dirty[2][DIRTY_MAX];            // double-buffered by tile parity.  bit 15: f1/f2, else startw/shortw
     unsigned long long s0, rec0;
@@ -155,29 +152,6 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, 
         uint32_t s = wsum[i];
         if (i < warp) pre += s;
         tot += s;
-    }
-    total = tot;
-    return pre + incl - v;
-}
-__device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long v, unsigned long long *wsum,
-                                                                unsigned long long &total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    __syncthreads();
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    unsigned long long pre = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < NT / 32; ++i) {
-        const unsigned long long x = wsum[i];
-        if (i < warp) pre += x;
-        tot += x;
     }
     total = tot;
     return pre + incl - v;
@@ -315,24 +289,26 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const uint32_t lb = A.tile_lb[t];
         const uint32_t ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
 
-        // ---- S3a: this thread's raw bases, global -> registers: four 16-byte pieces, piece m at window offset
-        //      4096*m + 16*tid (coalesced).  Issued first: the latency overlaps S2.
+        // ---- S3a: this thread's 64 raw bases, global -> registers (issued first: the latency overlaps S2)
+        const int64_t g0 = W0 + RAWPT * tid;
         uint32_t w[16];
+        if (g0 >= 0 && g0 + RAWPT <= (int64_t)A.n_bases) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.bases + g0);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int64_t g = W0 + SEG * m + 16 * tid;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (g >= 0 && g + 16 <= (int64_t)A.n_bases) {
-                x = __ldg(reinterpret_cast<const uint4 *>(A.bases + g));
-            } else if (g + 16 > 0 && g < (int64_t)A.n_bases) {
-                uint32_t t4[4] = {0, 0, 0, 0};
-                for (int j = 0; j < 16; ++j) {
-                    const int64_t gg = g + j;
-                    if (gg >= 0 && gg < (int64_t)A.n_bases) t4[j >> 2] |= (uint32_t)A.bases[gg] << (8 * (j & 3));
-                }
-                x = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+            for (int v = 0; v < 4; ++v) {
+                const uint4 x = __ldg(src + v);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
             }
-            w[4 * m] = x.x; w[4 * m + 1] = x.y; w[4 * m + 2] = x.z; w[4 * m + 3] = x.w;
+        } else {
+#pragma unroll
+            for (int v = 0; v < 16; ++v) {
+                uint32_t x = 0;
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t gg = g0 + 4 * v + j;
+                    if (gg >= 0 && gg < (int64_t)A.n_bases) x |= (uint32_t)A.bases[gg] << (8 * j);
+                }
+                w[v] = x;
+            }
         }
 
         // ---- S2: sequence starts inside the tile (and the start of the sequence containing T0, if in the window)
@@ -356,98 +332,61 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         }
         __syncthreads();
 
-        // ---- S3b: keep mask per piece, one block scan of the four kept counts (packed 4 x 16 bit)
-        uint32_t km[4];
-        unsigned long long packed = 0ull;
+        // ---- S3b: keep mask, block scan of kept counts
+        uint32_t klo, khi;
+        if (HPC) {
+            uint32_t prevb = __shfl_up_sync(0xffffffffu, w[15] >> 24, 1);
+            if (lane == 0) prevb = (g0 > 0 && g0 <= (int64_t)A.n_bases) ? A.bases[g0 - 1] : 0u;
+            uint32_t kk[2] = {0u, 0u};
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int64_t g = W0 + SEG * m + 16 * tid;
-            uint32_t k16;
-            const uint32_t sbits = (S.startw[(SEG / 32) * m + (tid >> 1)] >> (16 * (tid & 1))) & 0xffffu;
-            if (HPC) {
-                uint32_t prevb = __shfl_up_sync(0xffffffffu, w[4 * m + 3] >> 24, 1);
-                if (lane == 0) prevb = (g > 0 && g <= (int64_t)A.n_bases) ? A.bases[g - 1] : 0u;
-                k16 = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t sh = (w[4 * m + i] << 8) | prevb;
-                    prevb = w[4 * m + i] >> 24;
-                    const uint32_t neq = __vcmpne4(w[4 * m + i], sh);
-                    k16 |= (((neq & 0x08040201u) * 0x01010101u) >> 24) << (4 * i);
-                }
-                k16 |= sbits;
-            } else {
-                k16 = 0xffffu;
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t sh = (w[i] << 8) | prevb;
+                prevb = w[i] >> 24;
+                const uint32_t neq = __vcmpne4(w[i], sh);
+                kk[i >> 3] |= (((neq & 0x08040201u) * 0x01010101u) >> 24) << (4 * (i & 7));
             }
-            uint32_t vmask = 0xffffu;
-            if (g < 0) vmask = (g <= -16) ? 0u : ((0xffffu << (int)(-g)) & 0xffffu);
-            const int64_t rem = T1 - g;
-            if (rem <= 0) vmask = 0u; else if (rem < 16) vmask &= (1u << (int)rem) - 1u;
-            km[m] = k16 & vmask;
-            packed |= (unsigned long long)__popc(km[m]) << (16 * m);
+            klo = kk[0] | S.startw[2 * tid];
+            khi = kk[1] | S.startw[2 * tid + 1];
+        } else {
+            klo = khi = 0xffffffffu;
         }
-        uint32_t qm[4];
-        uint32_t wk;
         {
-            unsigned long long tot;
-            const unsigned long long ex = block_excl_scan64(packed, S.wsum64, tot);
-            uint32_t segbase = 0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                qm[m] = segbase + (uint32_t)((ex >> (16 * m)) & 0xffffu);
-                segbase += (uint32_t)((tot >> (16 * m)) & 0xffffu);
-            }
-            wk = segbase;
+            unsigned long long vmask = ~0ull;
+            if (g0 < 0) vmask = (g0 <= -64) ? 0ull : (~0ull << (int)(-g0));
+            const int64_t rem = T1 - g0;
+            if (rem <= 0) vmask = 0ull; else if (rem < 64) vmask &= (1ull << (int)rem) - 1ull;
+            klo &= (uint32_t)vmask; khi &= (uint32_t)(vmask >> 32);
         }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            reinterpret_cast<uint16_t *>(S.keepw)[2 * (SEG / 32) * m + tid] = (uint16_t)km[m];
-            if (!(tid & 1)) S.qoff[(SEG / 32) * m + (tid >> 1)] = qm[m];
-            const uint32_t c = __popc(km[m]);
-            const uint32_t mm = (qm[m] + 63u) & ~63u;       // at most one multiple of 64 among <= 16 kept indices
-            if (mm < qm[m] + c) S.qmap[mm >> 6] = (uint16_t)((SEG / 32) * m + (tid >> 1));
-        }
+        const uint32_t clo = __popc(klo);
+        uint32_t wk;
+        const uint32_t q = block_excl_scan(clo + __popc(khi), S.wsum, wk);
+        S.keepw[2 * tid] = klo; S.keepw[2 * tid + 1] = khi;
+        S.qoff[2 * tid] = q; S.qoff[2 * tid + 1] = q + clo;
         if (tid == NT - 1) { S.qoff[NCHUNK] = wk; S.keepw[NCHUNK] = 0; }
+        if (tid == (int)(A.halo >> 6)) S.hk = ((A.halo >> 5) & 1u) ? q + clo : q;
+        for (uint32_t m = (q + 63u) & ~63u; m < q + clo + __popc(khi); m += 64)
+            S.qmap[m >> 6] = (uint16_t)(m < q + clo ? 2 * tid : 2 * tid + 1);
 
-        // ---- S4: compaction (predicated byte stores in HPC order; lane stride ~12 bytes = 3 words: conflict-free)
+        // ---- S4: compaction (predicated byte stores in HPC order)
+        {
+            uint8_t *cp = S.code + XB + q;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            uint8_t *cp = S.code + XB + qm[m];
-            if (HPC) {
-#pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    if ((km[m] >> b) & 1u) { *cp = S.lut[(w[4 * m + (b >> 2)] >> (8 * (b & 3))) & 0xffu]; ++cp; }
-                }
-            } else {                                     // every valid base is kept: one 16-byte store per piece
-                uint32_t o4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t x = w[4 * m + i];
-                    o4[i] = (uint32_t)S.lut[x & 0xffu] | ((uint32_t)S.lut[(x >> 8) & 0xffu] << 8) |
-                            ((uint32_t)S.lut[(x >> 16) & 0xffu] << 16) | ((uint32_t)S.lut[x >> 24] << 24);
-                }
-                if (km[m] == 0xffffu && ((XB + qm[m]) & 15u) == 0) {
-                    *reinterpret_cast<uint4 *>(cp) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 16; ++b)
-                        if ((km[m] >> b) & 1u) { *cp = (uint8_t)(o4[b >> 2] >> (8 * (b & 3))); ++cp; }
-                }
+            for (int b = 0; b < 64; ++b) {
+                const uint32_t kb = (b < 32 ? (klo >> b) : (khi >> (b - 32))) & 1u;
+                if (kb) { *cp = S.lut[(w[b >> 2] >> (8 * (b & 3))) & 0xffu]; ++cp; }
             }
         }
         __syncthreads();
-        const uint32_t hk = S.qoff[A.halo >> 5];
-        // sequence starts among this thread's kept bases -> owner-space flags (rare)
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int wi = (SEG / 32) * m + (tid >> 1), sh16 = 16 * (tid & 1);
-            uint32_t sw = ((S.startw[wi] >> sh16) & 0xffffu) & km[m];
-            const uint32_t sh2 = (S.shortw[wi] >> sh16) & 0xffffu;
+        const uint32_t hk = S.hk;
+        {   // sequence starts among this thread's kept bases -> owner-space flags (rare)
+            const unsigned long long keep = ((unsigned long long)khi << 32) | klo;
+            unsigned long long sw = (((unsigned long long)S.startw[2 * tid + 1] << 32) | S.startw[2 * tid]) & keep;
+            const unsigned long long sh2 = ((unsigned long long)S.shortw[2 * tid + 1] << 32) | S.shortw[2 * tid];
             while (sw) {
-                const int b = __ffs(sw) - 1;
+                const int b = __ffsll((long long)sw) - 1;
                 sw &= sw - 1;
-                const int oo = (int)qm[m] + __popc(km[m] & lowmask(b)) - (int)hk + XB;
-                if (oo >= 0) flag_owner(S, par, oo, (sh2 >> b) & 1u);
+                const int oo = (int)q + __popcll(keep & lowmask64(b)) - (int)hk + XB;
+                if (oo >= 0) flag_owner(S, par, oo, (sh2 >> b) & 1ull);
             }
         }
         // ---- S4b: not enough context in the halo -> walk back through the sequence (rare: long homopolymers)
@@ -514,45 +453,23 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                             }
                         }
                     }
-                    // Class codes are read as aligned words (13-word lane stride: conflict-free) and picked apart
-                    // with PRMT.  ci = index of the code of owner 0's last base; the entering stream starts there,
-                    // the leaving stream l codes earlier; both have the same alignment in every lane.
-                    const int ci = XB + (int)hk + v0 - d, co_ = ci - l;
-                    const uint32_t *wi = reinterpret_cast<const uint32_t *>(S.code + (ci & ~3));
-                    const uint32_t *wo = reinterpret_cast<const uint32_t *>(S.code + (co_ & ~3));
-                    const uint32_t ai = 8u * (ci & 3), ao = 8u * (co_ & 3);
+                    const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer
                     uint32_t fh = 0, rh = 0;
-                    {   // warm-up: the l-1 codes before ci, taken four at a time; codes in front of them count as the
-                        // zero class, which leaves the all-zero state unchanged
-                        const int ng = (l - 1 + 3) >> 2;
-                        const uint32_t *wp = wi - ng;
-                        uint32_t lo = wp[0];
-                        for (int g = 0; g < ng; ++g) {
-                            const uint32_t hi = wp[g + 1];
-                            const uint32_t cw = __funnelshift_r(lo, hi, ai);
-                            lo = hi;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                uint32_t in8 = __byte_perm(cw, 0, 0x4440 + k);
-                                if (4 * (g - ng) + k < 1 - l) in8 = ZC8;
-                                const uint2 tt = xy_at(S, ZC8, in8);
-                                fh = rol1<W31>(fh) ^ tt.x;
-                                rh = ror1<W31>(rh) ^ tt.y;
-                            }
-                        }
+                    for (int j = 1 - l; j < 0; ++j) {                  // warm-up: first l-1 bases of owner 0's l-mer
+                        const uint2 tt = xy_at(S, ZC8, cb[j]);
+                        fh = rol1<W31>(fh) ^ tt.x;
+                        rh = ror1<W31>(rh) ^ tt.y;
                     }
+                    const uint8_t *co = cb - l;
                     static_assert(CH % 4 == 0, "hits are tested once per group of four owners");
-                    uint32_t ilo = wi[0], olo = wo[0];
 #pragma unroll
-                    for (int g = 0; g < CH / 4; ++g) {
-                        const uint32_t ihi = wi[g + 1], ohi = wo[g + 1];
-                        const uint32_t iw = __funnelshift_r(ilo, ihi, ai), ow = __funnelshift_r(olo, ohi, ao);
-                        ilo = ihi; olo = ohi;
+                    for (int i0 = 0; i0 < CH; i0 += 4) {
                         uint32_t hv[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint32_t in8 = __byte_perm(iw, 0, 0x4440 + k);
-                            const uint32_t out8 = (g == 0 && k == 0) ? (uint32_t)ZC8 : __byte_perm(ow, 0, 0x4440 + k);
+                            const int i = i0 + k;
+                            const uint32_t in8 = cb[i];
+                            const uint32_t out8 = i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8;
                             const uint2 tt = xy_at(S, out8, in8);
                             fh = rol1<W31>(fh) ^ tt.x;
                             rh = ror1<W31>(rh) ^ tt.y;
@@ -561,7 +478,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                         if (min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= A.thr) {   // rare: ~8 % of groups at d=0.01
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                if (hv[k] <= A.thr) { mask |= 1ull << (4 * g + k); hs[v0 + 4 * g + k] = hv[k]; }
+                                if (hv[k] <= A.thr) { mask |= 1ull << (i0 + k); hs[v0 + i0 + k] = hv[k]; }
                         }
                     }
                     mask &= ~invalid & lowmask64((uint32_t)n_u);     // owners >= n_u hashed garbage
