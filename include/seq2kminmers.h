@@ -122,6 +122,10 @@ int  s2k_ctx_set_flags(s2k_ctx *ctx, uint32_t flags);
 int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs,
             const s2k_params *params, s2k_result *out);
 
+/* Large host batches are streamed through the device in slabs cut at sequence boundaries (H2D, kernels and D2H
+ * overlap on three streams).  bytes = target slab size (0 = default 256 MiB); batches up to 1.5 slabs go in one piece. */
+int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes);
+
 /* Same, DEVICE buffers already resident in HBM (bases 16-byte aligned); results stay on the device.
  * `stream` is a cudaStream_t (NULL = the context's own stream).  Returns after the launch sequence has been
  * enqueued and the two scalar totals have been read back (one stream synchronisation). */

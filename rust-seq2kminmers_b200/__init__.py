@@ -81,6 +81,7 @@ ABI_SYMBOLS = (
     "s2k_ctx_create", "s2k_ctx_destroy", "s2k_ctx_set_flags", "s2k_run", "s2k_run_device", "s2k_encode_rle",
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
+    "s2k_ctx_set_slab_bytes",
 )
 
 
@@ -123,6 +124,8 @@ class Library:
         L.s2k_launch_count.argtypes = [vp]
         L.s2k_ctx_set_timing.restype = C.c_int
         L.s2k_ctx_set_timing.argtypes = [vp, C.c_int]
+        L.s2k_ctx_set_slab_bytes.restype = C.c_int
+        L.s2k_ctx_set_slab_bytes.argtypes = [vp, C.c_uint64]
         L.s2k_synth_device.restype = C.c_int
         L.s2k_synth_device.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
         L.s2k_last_kernel_ms.restype = C.c_int
@@ -298,6 +301,10 @@ class Context:
         self._check(self.lib.c.s2k_encode_rle(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(r)))
         return (_view(r.hpc, r.n_hpc, np.uint8).copy(), _view(r.pos, r.n_hpc, np.uint32).copy(),
                 _view(r.hpc_off, n + 1, np.uint64).copy())
+
+    def set_slab_bytes(self, nbytes: int):
+        """Target slab size of the pipelined host path (0 = default 256 MiB)."""
+        self._check(self.lib.c.s2k_ctx_set_slab_bytes(self.h, int(nbytes)))
 
     def set_timing(self, enabled: bool):
         self._check(self.lib.c.s2k_ctx_set_timing(self.h, 1 if enabled else 0))

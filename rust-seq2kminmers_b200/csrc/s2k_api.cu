@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 using namespace s2k;
 
@@ -90,6 +91,12 @@ struct s2k_ctx {
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
     bool attr_set = false;
+    // pipelined host path (s2k_run on large batches)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_out = nullptr, ev_done = nullptr;
+    bool pipe_ready = false;
+    uint64_t slab_bytes = 0;        // 0 = default
+    Buf d_in[2], d_in_off[2], h_off_stage[2];
 };
 
 namespace {
@@ -129,6 +136,18 @@ int ensure(s2k_ctx *ctx, Buf &b, size_t bytes, bool host)
                                           cudaGetErrorString(e));
     }
     b.cap = want; b.host = host;
+    return S2K_OK;
+}
+// Grow a pinned host buffer, keeping its first `keep` bytes.
+int ensure_keep(s2k_ctx *ctx, Buf &b, size_t bytes, size_t keep)
+{
+    if (bytes <= b.cap && b.p) return S2K_OK;
+    Buf nb;
+    int rc = ensure(ctx, nb, bytes + bytes / 4, true);
+    if (rc != S2K_OK) return rc;
+    if (b.p && keep) std::memcpy(nb.p, b.p, keep);
+    if (b.p) cudaFreeHost(b.p);
+    b = nb;
     return S2K_OK;
 }
 void release(Buf &b)
@@ -470,11 +489,17 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
                   &ctx->d_min_off, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
                   &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
-                  &ctx->h_rle_hpc, &ctx->h_rle_pos};
+                  &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in_off[0], &ctx->d_in_off[1],
+                  &ctx->h_off_stage[0], &ctx->h_off_stage[1]};
     for (Buf *b : all) release(*b);
     if (ctx->tm.created) {
         for (auto &e : ctx->tm.ev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
         cudaEventDestroy(ctx->tm.wv[0]); cudaEventDestroy(ctx->tm.wv[1]);
+    }
+    if (ctx->pipe_ready) {
+        cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_free[i]); }
+        cudaEventDestroy(ctx->ev_out); cudaEventDestroy(ctx->ev_done);
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -547,6 +572,144 @@ int s2k_run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_o
     return run_device(ctx, d_bases, d_seq_off, n_seqs, n_bases, P, st, out);
 }
 
+int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    ctx->slab_bytes = bytes;
+    return S2K_OK;
+}
+
+// Large host batches: slabs cut at sequence boundaries flow through H2D -> kernels -> D2H on three streams, so that
+// both PCIe directions and the compute overlap.  Input slabs are double-buffered on the device; the device result
+// buffers are single (a slab's D2H is long finished when the next slab's H2D completes).
+static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const Plan &P,
+                         uint64_t slab_bytes, s2k_result *out)
+{
+    int rc;
+    if (!ctx->pipe_ready) {
+        CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) { CU(cudaEventCreate(&ctx->ev_in[i])); CU(cudaEventCreate(&ctx->ev_free[i])); }
+        CU(cudaEventCreate(&ctx->ev_out)); CU(cudaEventCreate(&ctx->ev_done));
+        ctx->pipe_ready = true;
+    }
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_bases = seq_off[n_seqs];
+    const bool want_min = (ctx->flags & S2K_WANT_MINIMIZERS) != 0;
+    // slab boundaries (sequence indices)
+    std::vector<uint64_t> cut{0};
+    uint64_t max_b = 0, max_n = 0;
+    while (cut.back() < n_seqs) {
+        const uint64_t r0 = cut.back();
+        const uint64_t *e = std::upper_bound(seq_off + r0 + 1, seq_off + n_seqs + 1, seq_off[r0] + slab_bytes);
+        uint64_t r1 = (uint64_t)(e - seq_off) - 1;
+        if (r1 <= r0) r1 = r0 + 1;                       // a sequence longer than a slab travels whole
+        if (r1 > n_seqs) r1 = n_seqs;
+        cut.push_back(r1);
+        max_b = std::max(max_b, seq_off[r1] - seq_off[r0]);
+        max_n = std::max(max_n, r1 - r0);
+    }
+    const size_t n_slabs = cut.size() - 1;
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = ensure(ctx, ctx->d_in[i], max_b + 16, false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_in_off[i], (max_n + 1) * 8, false))) return rc;
+        if ((rc = ensure(ctx, ctx->h_off_stage[i], (max_n + 1) * 8, true))) return rc;
+    }
+    if ((rc = ensure(ctx, ctx->h_km_off, (n_seqs + 1) * 8, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_min_off, (n_seqs + 1) * 8, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_min_cnt, std::max<uint64_t>(n_seqs, 1) * 4, true))) return rc;
+
+    auto issue_h2d = [&](size_t s) -> int {
+        const int b = (int)(s & 1);
+        const uint64_t r0 = cut[s], r1 = cut[s + 1], nb = seq_off[r1] - seq_off[r0];
+        CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_free[b], 0));          // the kernels of slab s-2 are done with it
+        uint64_t *stage = ptr<uint64_t>(ctx->h_off_stage[b]);
+        for (uint64_t i = 0; i <= r1 - r0; ++i) stage[i] = seq_off[r0 + i] - seq_off[r0];
+        if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, bases + seq_off[r0], nb, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CU(cudaMemcpyAsync(ctx->d_in_off[b].p, stage, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CU(cudaEventRecord(ctx->ev_in[b], ctx->s_h2d));
+        return S2K_OK;
+    };
+
+    uint64_t items = 0, mins = 0;
+    CU(cudaEventRecord(ctx->ev_free[0], st));
+    CU(cudaEventRecord(ctx->ev_free[1], st));
+    CU(cudaEventRecord(ctx->ev_out, ctx->s_d2h));
+    if ((rc = issue_h2d(0))) return rc;
+    for (size_t s = 0; s < n_slabs; ++s) {
+        const int b = (int)(s & 1);
+        const uint64_t r0 = cut[s], r1 = cut[s + 1], ns = r1 - r0, nb = seq_off[r1] - seq_off[r0];
+        if (s + 1 < n_slabs) {
+            // the staging buffer of slab s+1 was last read by the H2D of slab s-1: wait for that copy on the host
+            if (s >= 1) CU(cudaEventSynchronize(ctx->ev_in[(s + 1) & 1]));
+            if ((rc = issue_h2d(s + 1))) return rc;
+        }
+        CU(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));                    // inputs of this slab have landed
+        CU(cudaStreamWaitEvent(st, ctx->ev_out, 0));                      // results of the previous slab have left
+        s2k_result dev;
+        rc = run_device(ctx, ptr<uint8_t>(ctx->d_in[b]), ptr<uint64_t>(ctx->d_in_off[b]), ns, nb, P, st, &dev);
+        if (rc != S2K_OK) return rc;
+        // per-slab prefixes / sequence indices -> global
+        const int g1 = (int)std::min<uint64_t>((ns + 256) / 256, (uint64_t)ctx->sm_count * 8);
+        if (items) S2K_LAUNCH(k_add_u64, g1, 256, 0, st, false, const_cast<uint64_t *>(dev.km_off), ns + 1, items);
+        if (mins) S2K_LAUNCH(k_add_u64, g1, 256, 0, st, false, const_cast<uint64_t *>(dev.min_off), ns + 1, mins);
+        if (want_min && r0 && dev.n_minimizers) {
+            const int g2 = (int)std::min<uint64_t>((dev.n_minimizers + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            S2K_LAUNCH(k_add_seq, g2, 256, 0, st, false, reinterpret_cast<uint4 *>(const_cast<s2k_minimizer *>(dev.minimizers)),
+                       dev.n_minimizers, (uint32_t)r0);
+        }
+        CU(cudaEventRecord(ctx->ev_free[b], st));
+        CU(cudaEventRecord(ctx->ev_done, st));
+        // host result buffers: sized from the first slab's rates, grown (rarely) if a later slab is denser
+        const uint64_t ni = dev.n_items, nm = dev.n_minimizers;
+        uint64_t need_i = items + ni, need_m = mins + nm;
+        if (s == 0 && nb) {
+            const double scale = (double)n_bases / (double)nb * 1.03;
+            need_i = std::max<uint64_t>(need_i, (uint64_t)((double)ni * scale) + 65536);
+            need_m = std::max<uint64_t>(need_m, (uint64_t)((double)nm * scale) + 65536);
+        }
+        if (need_i * 8 > ctx->h_hash.cap || need_i * 4 > ctx->h_start.cap || need_i * 4 > ctx->h_end.cap || need_i > ctx->h_rev.cap ||
+            (want_min && need_m * 16 > ctx->h_mins.cap)) {
+            CU(cudaStreamSynchronize(ctx->s_d2h));                        // earlier copies must have landed before moving
+            if ((rc = ensure_keep(ctx, ctx->h_hash, std::max<uint64_t>(need_i, 1) * 8, items * 8))) return rc;
+            if ((rc = ensure_keep(ctx, ctx->h_start, std::max<uint64_t>(need_i, 1) * 4, items * 4))) return rc;
+            if ((rc = ensure_keep(ctx, ctx->h_end, std::max<uint64_t>(need_i, 1) * 4, items * 4))) return rc;
+            if ((rc = ensure_keep(ctx, ctx->h_rev, std::max<uint64_t>(need_i, 1), items))) return rc;
+            if (want_min && (rc = ensure_keep(ctx, ctx->h_mins, std::max<uint64_t>(need_m, 1) * 16, mins * 16))) return rc;
+        }
+        cudaStream_t so = ctx->s_d2h;
+        CU(cudaStreamWaitEvent(so, ctx->ev_done, 0));
+        if (ni) {
+            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_hash) + items, dev.hash, ni * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_start) + items, dev.start, ni * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_end) + items, dev.end, ni * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_rev) + items, dev.rev, ni, cudaMemcpyDeviceToHost, so));
+        }
+        const uint64_t tail = (s + 1 == n_slabs) ? 1 : 0;                  // the last slab also brings the final prefix
+        CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_km_off) + r0, dev.km_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
+        CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_min_off) + r0, dev.min_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
+        if (ns) CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_min_cnt) + r0, dev.min_cnt, ns * 4, cudaMemcpyDeviceToHost, so));
+        if (want_min && nm)
+            CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_mins) + mins * 16, dev.minimizers, nm * 16, cudaMemcpyDeviceToHost, so));
+        CU(cudaEventRecord(ctx->ev_out, so));
+        items += ni; mins += nm;
+    }
+    CU(cudaStreamSynchronize(ctx->s_d2h));
+    CU(cudaStreamSynchronize(ctx->s_h2d));
+    std::memset(out, 0, sizeof(*out));
+    out->n_seqs = n_seqs; out->n_items = items; out->n_minimizers = mins;
+    out->location = S2K_LOC_HOST;
+    out->hash = ptr<uint64_t>(ctx->h_hash);
+    out->start = ptr<uint32_t>(ctx->h_start);
+    out->end = ptr<uint32_t>(ctx->h_end);
+    out->rev = ptr<uint8_t>(ctx->h_rev);
+    out->km_off = ptr<uint64_t>(ctx->h_km_off);
+    out->min_off = ptr<uint64_t>(ctx->h_min_off);
+    out->min_cnt = ptr<uint32_t>(ctx->h_min_cnt);
+    out->minimizers = want_min ? reinterpret_cast<const s2k_minimizer *>(ctx->h_mins.p) : nullptr;
+    return S2K_OK;
+}
+
 int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const s2k_params *params,
             s2k_result *out)
 {
@@ -561,6 +724,10 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
     CU(cudaSetDevice(ctx->device));
     ctx->err.clear();
     cudaStream_t st = ctx->stream;
+    {
+        const uint64_t slab = ctx->slab_bytes ? ctx->slab_bytes : (256ull << 20);
+        if (n_bases > slab + slab / 2 && n_seqs > 1) return run_pipelined(ctx, bases, seq_off, n_seqs, P, slab, out);
+    }
     if ((rc = ensure(ctx, ctx->d_bases, n_bases + 16, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_seq_off, (n_seqs + 1) * 8, false))) return rc;
     if (n_bases) CU(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));

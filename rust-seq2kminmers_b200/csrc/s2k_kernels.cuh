@@ -893,6 +893,20 @@ __global__ void __launch_bounds__(NT) k_rle(const __grid_constant__ K4Args A)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ slab stitching
+// s2k_run streams a large host batch through the device in slabs; per-slab prefixes and sequence indices are made
+// global on the device before they are copied back.
+__global__ void k_add_u64(uint64_t *__restrict__ a, uint64_t n, uint64_t add)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] += add;
+}
+__global__ void k_add_seq(uint4 *__restrict__ mins, uint64_t n, uint32_t add)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mins[i].w += add;
+}
+
 // ------------------------------------------------------------------------------------------------ synthetic reads
 // Workload generator of SURVEY.md 8(d): 32 bases per 64-bit word, word(j) = splitmix64 finalizer of
 // seed + (j+1)*0x9E3779B97F4A7C15, base(i) = "ACGT"[(word(i>>5) >> 2*(i&31)) & 3].  Same data on host

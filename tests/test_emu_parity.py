@@ -59,3 +59,15 @@ def test_error_codes_mirror_reference_panics(S, emu_ctx):
     assert e.value.status == -5
     empty = emu_ctx.run(b[:0], np.array([0], dtype=np.uint64), 5, 2, 0.1, S.HashMode.Hpc)
     assert empty.n_items == 0 and empty.n_seqs == 0
+
+
+def test_pipelined_host_path_emulated(S, O, emu_ctx, batches):
+    """s2k_run on a batch larger than 1.5 slabs: slabs cut at sequence boundaries, offsets and sequence indices stitched."""
+    bases, so = batches.batch([9000, 150, 0, 20000, 31, 7000, 0, 0, 12000, 150, 150, 30000, 5])
+    emu_ctx.set_slab_bytes(10000)
+    try:
+        for mode in (S.HashMode.HpcSimd, S.HashMode.Regular):
+            got = emu_ctx.run(bases, so, 31, 3, 0.03, mode, want_minimizers=True)
+            assert_batch_matches_oracle(O, got, bases, so, 31, 3, 0.03, mode)
+    finally:
+        emu_ctx.set_slab_bytes(0)

@@ -154,3 +154,16 @@ def test_cpp_host_wrapper_twin_of_reference_test(S, tmp_path):
                     f"-L{S.PKG_DIR}", "-l:libs2k_b200.so", f"-Wl,-rpath,{S.PKG_DIR}"], check=True)
     out = subprocess.run([str(exe), str(ROOT / "tests" / "golden" / "ecoli100k.2bit")], capture_output=True, text=True)
     assert out.returncode == 0 and "test_main ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_pipelined_host_path(S, O, gpu_ctx, batches):
+    """s2k_run streaming a batch through the device in many small slabs (three streams) == the oracle."""
+    lens = [9000, 150, 0, 20000, 31, 7000, 0, 0, 12000, 150, 150, 30000, 5] * 6
+    bases, so = batches.batch(lens)
+    gpu_ctx.set_slab_bytes(40000)
+    try:
+        for mode in (S.HashMode.HpcSimd, S.HashMode.Hpc, S.HashMode.Simd):
+            got = gpu_ctx.run(bases, so, 31, 3, 0.03, mode, want_minimizers=True)
+            assert_batch_matches_oracle(O, got, bases, so, 31, 3, 0.03, mode)
+    finally:
+        gpu_ctx.set_slab_bytes(0)
