@@ -285,7 +285,6 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     const int max_grid = ctx->sm_count * S2K_MINB;
     if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_tile_base, ((uint64_t)n_tiles + 1) * 16, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_hscr, (size_t)max_grid * WIN * 4, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_status, ((n_seqs + RT * RPT - 1) / (RT * RPT)) * 8 + 8, false))) return rc;
 
@@ -329,10 +328,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         S2K_LAUNCH(kfn, grid, NT, smem, st, true, A);
         if (rec) { cudaEventRecord(T.ev[T.n][1], st); ++T.n; }
         CU(cudaGetLastError());
-        S2K_LAUNCH(k_tile_scan, 1, ST, 0, st, false, ptr<uint4>(ctx->d_tile_info), n_tiles, ptr<ulonglong2>(ctx->d_tile_base));
-        CU(cudaGetLastError());
-        ctx->launches += 2;
-        CU(cudaMemcpyAsync(hsmall, ptr<ulonglong2>(ctx->d_tile_base) + n_tiles, 16, cudaMemcpyDeviceToHost, st));
+        ctx->launches += 1;
+        CU(cudaMemcpyAsync(hsmall, small, 8, cudaMemcpyDeviceToHost, st));          // record cursor == total minimizers
         CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         n_min = hsmall[0];
@@ -342,13 +339,19 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     }
     if ((rc = ensure(ctx, ctx->d_mins, std::max<uint64_t>(n_min, 1) * sizeof(uint4), false))) return rc;
     {
+        const uint32_t n_chunks = (n_tiles + FT - 1) / FT;
+        if ((rc = ensure(ctx, ctx->d_tile_base, (uint64_t)n_chunks * 16 + 16, false))) return rc;
         KFArgs F;
-        F.tile_info = ptr<uint4>(ctx->d_tile_info); F.tile_base = ptr<ulonglong2>(ctx->d_tile_base);
+        F.tile_info = ptr<uint4>(ctx->d_tile_info);
         F.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
         F.min_off = ptr<uint64_t>(ctx->d_min_off); F.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+        F.status_a = ptr<uint64_t>(ctx->d_tile_base); F.status_b = F.status_a + n_chunks;
+        F.ticket = reinterpret_cast<uint32_t *>(small + 6); F.err = reinterpret_cast<uint32_t *>(small + 5);
         F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = cap; F.n_tiles = n_tiles; F.tile = P.tile;
-        const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 8);
-        S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
+        CU(cudaMemsetAsync(F.status_a, 0, (uint64_t)n_chunks * 16, st));
+        CU(cudaMemsetAsync(F.ticket, 0, 4, st));
+        const int gridf = (int)std::min<uint64_t>(n_chunks, (uint64_t)ctx->sm_count * 4);
+        S2K_LAUNCH(k_finalize, gridf, FT, 0, st, false, F);
         CU(cudaGetLastError());
         ctx->launches += 1;
     }
@@ -385,7 +388,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);
         C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
         if (n_min > 0) {
-            const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 16);
+            const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 8);
             S2K_LAUNCH(k_windows, g3, 256, 0, st, false, C);
             CU(cudaGetLastError());
             ctx->launches += 1;
@@ -613,7 +616,6 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     for (int i = 0; i < 2; ++i) {
         if ((rc = ensure(ctx, ctx->d_in[i], max_b + 16, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_in_off[i], (max_n + 1) * 8, false))) return rc;
-        if ((rc = ensure(ctx, ctx->h_off_stage[i], (max_n + 1) * 8, true))) return rc;
     }
     if ((rc = ensure(ctx, ctx->h_km_off, (n_seqs + 1) * 8, true))) return rc;
     if ((rc = ensure(ctx, ctx->h_min_off, (n_seqs + 1) * 8, true))) return rc;
@@ -623,10 +625,16 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
         const int b = (int)(s & 1);
         const uint64_t r0 = cut[s], r1 = cut[s + 1], nb = seq_off[r1] - seq_off[r0];
         CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_free[b], 0));          // the kernels of slab s-2 are done with it
-        uint64_t *stage = ptr<uint64_t>(ctx->h_off_stage[b]);
-        for (uint64_t i = 0; i <= r1 - r0; ++i) stage[i] = seq_off[r0 + i] - seq_off[r0];
         if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, bases + seq_off[r0], nb, cudaMemcpyHostToDevice, ctx->s_h2d));
-        CU(cudaMemcpyAsync(ctx->d_in_off[b].p, stage, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+        // offsets: copy the caller's slice as it is, rebase it to the slab on the device
+        uint64_t *d_off = ptr<uint64_t>(ctx->d_in_off[b]);
+        CU(cudaMemcpyAsync(d_off, seq_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (r0) {
+            const int g = (int)std::min<uint64_t>((r1 - r0 + 256) / 256, (uint64_t)ctx->sm_count * 4);
+            S2K_LAUNCH(k_sub_first, g, 256, 0, ctx->s_h2d, false, d_off, r1 - r0 + 1);
+            S2K_LAUNCH(k_zero_first, 1, 1, 0, ctx->s_h2d, false, d_off);
+            ctx->launches += 2;
+        }
         CU(cudaEventRecord(ctx->ev_in[b], ctx->s_h2d));
         return S2K_OK;
     };
@@ -640,8 +648,6 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
         const int b = (int)(s & 1);
         const uint64_t r0 = cut[s], r1 = cut[s + 1], ns = r1 - r0, nb = seq_off[r1] - seq_off[r0];
         if (s + 1 < n_slabs) {
-            // the staging buffer of slab s+1 was last read by the H2D of slab s-1: wait for that copy on the host
-            if (s >= 1) CU(cudaEventSynchronize(ctx->ev_in[(s + 1) & 1]));
             if ((rc = issue_h2d(s + 1))) return rc;
         }
         CU(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));                    // inputs of this slab have landed

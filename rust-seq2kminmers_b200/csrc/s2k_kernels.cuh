@@ -37,14 +37,26 @@
 namespace s2k {
 
 // ------------------------------------------------------------------------------------------------ geometry
-constexpr int NT    = 256;          // threads per CTA
+#ifndef S2K_NT
+#define S2K_NT 256
+#endif
+constexpr int NT    = S2K_NT;       // threads per CTA
 constexpr int RAWPT = 64;           // raw bases per thread in the keep/compaction phase
 constexpr int WIN   = NT * RAWPT;   // raw bases staged per tile (left halo + tile)
 constexpr int NCHUNK = WIN / 32;    // 32-base chunks per window
-constexpr int CH    = 52;           // owner positions per thread in the hash phase: 13 words, an odd word stride,
-                                    // so the per-lane byte streams of a warp fall into 32 different banks; with
-                                    // ~75 % of bases kept, 256 x 52 owners just cover a 16 128-base HPC tile
-constexpr int CAP   = NT * CH;      // owners hashed per pass (a second pass covers tiles that compress badly)
+#ifndef S2K_CH
+#define S2K_CH 52
+#endif
+#ifndef S2K_HT
+#define S2K_HT S2K_NT
+#endif
+constexpr int CH    = S2K_CH;       // owner positions per hash thread.  CH/4 must be odd: the per-lane byte streams of a
+                                    // warp then fall into 32 different banks.  (52: 13 words; 100: 25 words.)
+constexpr int HT    = S2K_HT;       // threads of the CTA that hash (the others wait at the barrier meanwhile)
+constexpr int MW    = (CH + 63) / 64;   // 64-bit words of a thread's hit mask
+constexpr int CAP   = HT * CH;      // owners hashed per pass (a second pass covers tiles that compress badly); with
+                                    // ~75 % of bases kept, CAP >= 12.1 k covers a 16 128-base HPC tile in one pass
+static_assert(CH % 4 == 0 && ((CH / 4) & 1) == 1 && CH <= 128 && HT <= NT && 2 * CAP >= WIN, "hash geometry");
 constexpr int XB    = 256;          // capacity of the left context, in kept (HPC) bases
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
 constexpr int HL    = 1024;         // hit-list entries emitted per round
@@ -84,7 +96,7 @@ struct K1Args {
 
 struct Smem {
     uint8_t  code[XB + WIN + 128];           // 8*class of every kept base, index XB + (kept index in the window)
-    unsigned long long hitw[2][NT + 1];      // per pass, per thread: selected owners (bit i = owner 60*t + i)
+    unsigned long long hitw[2][NT + 1][MW];  // per pass, per thread: selected owners (bit i = owner CH*t + i)
     uint32_t hitpre[2][NT + 1];              // ... and how many hits precede that thread in the tile
     uint32_t keepw[NCHUNK + 1];              // keep mask per 32-base chunk
     uint32_t qoff[NCHUNK + 1];               // kept bases before the chunk
@@ -422,74 +434,94 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         uint32_t tile_min = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
-            unsigned long long mask = 0ull;
+            unsigned long long mask[MW];
+#pragma unroll
+            for (int x = 0; x < MW; ++x) mask[x] = 0ull;
             const int v0 = pass * CAP + CH * tid;
             if ((uint32_t)(pass * CAP) >= n_own) {         // uniform: nothing left for this pass
-                S.hitw[pass][tid] = 0ull;
+#pragma unroll
+                for (int x = 0; x < MW; ++x) S.hitw[pass][tid][x] = 0ull;
                 S.hitpre[pass][tid] = tile_min;
-                if (tid == NT - 1) { S.hitw[pass][NT] = 0ull; S.hitpre[pass][NT] = tile_min; }
+                if (tid == NT - 1) {
+#pragma unroll
+                    for (int x = 0; x < MW; ++x) S.hitw[pass][NT][x] = 0ull;
+                    S.hitpre[pass][NT] = tile_min;
+                }
                 continue;
             }
-            {
-                if ((uint32_t)v0 < n_own) {
-                    const int n_u = min(CH, (int)n_own - v0);
-                    // owners invalidated by sequence starts: a start f kills owners [f, f+l-2+d] (+1 if len<=l)
-                    unsigned long long invalid = 0ull;
-                    {
-                        const int L1 = l - 1 + d, o0 = v0 + XB;
-                        const int w_hi = (o0 + CH - 1) >> 5, w_lo = (o0 - L1 - 1) >> 5;
-                        for (int wi = w_lo; wi <= w_hi; ++wi) {
-                            uint32_t fw = S.f1[wi];
-                            if (fw) {
-                                const uint32_t sw2 = S.f2[wi];
-                                while (fw) {
-                                    const int b = __ffs(fw) - 1;
-                                    fw &= fw - 1;
-                                    int lo = wi * 32 + b - o0;
-                                    int hi = lo + L1 + (int)((sw2 >> b) & 1u);
-                                    lo = max(lo, 0); hi = min(hi, 64);
-                                    if (hi > lo) invalid |= lowmask64(hi - lo) << lo;
+            if (tid < HT && (uint32_t)v0 < n_own) {
+                const int n_u = min(CH, (int)n_own - v0);
+                // owners invalidated by sequence starts: a start f kills owners [f, f+l-2+d] (+1 if len<=l)
+                unsigned long long invalid[MW];
+#pragma unroll
+                for (int x = 0; x < MW; ++x) invalid[x] = 0ull;
+                {
+                    const int L1 = l - 1 + d, o0 = v0 + XB;
+                    const int w_hi = (o0 + CH - 1) >> 5, w_lo = (o0 - L1 - 1) >> 5;
+                    for (int wi = w_lo; wi <= w_hi; ++wi) {
+                        uint32_t fw = S.f1[wi];
+                        if (fw) {
+                            const uint32_t sw2 = S.f2[wi];
+                            while (fw) {
+                                const int b = __ffs(fw) - 1;
+                                fw &= fw - 1;
+                                int lo = wi * 32 + b - o0;
+                                int hi = lo + L1 + (int)((sw2 >> b) & 1u);
+                                lo = max(lo, 0); hi = min(hi, CH);
+#pragma unroll
+                                for (int x = 0; x < MW; ++x) {
+                                    const int a = max(lo - 64 * x, 0), e = min(hi - 64 * x, 64);
+                                    if (e > a) invalid[x] |= lowmask64(e - a) << a;
                                 }
                             }
                         }
                     }
-                    const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer
-                    uint32_t fh = 0, rh = 0;
-                    for (int j = 1 - l; j < 0; ++j) {                  // warm-up: first l-1 bases of owner 0's l-mer
-                        const uint2 tt = xy_at(S, ZC8, cb[j]);
+                }
+                const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer
+                uint32_t fh = 0, rh = 0;
+                for (int j = 1 - l; j < 0; ++j) {                  // warm-up: first l-1 bases of owner 0's l-mer
+                    const uint2 tt = xy_at(S, ZC8, cb[j]);
+                    fh = rol1<W31>(fh) ^ tt.x;
+                    rh = ror1<W31>(rh) ^ tt.y;
+                }
+                const uint8_t *co = cb - l;
+#pragma unroll
+                for (int i0 = 0; i0 < CH; i0 += 4) {
+                    uint32_t hv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i0 + k;
+                        const uint32_t in8 = cb[i];
+                        const uint32_t out8 = i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8;
+                        const uint2 tt = xy_at(S, out8, in8);
                         fh = rol1<W31>(fh) ^ tt.x;
                         rh = ror1<W31>(rh) ^ tt.y;
+                        hv[k] = min(fh, rh);
                     }
-                    const uint8_t *co = cb - l;
-                    static_assert(CH % 4 == 0, "hits are tested once per group of four owners");
+                    if (min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= A.thr) {   // rare: ~8 % of groups at d=0.01
 #pragma unroll
-                    for (int i0 = 0; i0 < CH; i0 += 4) {
-                        uint32_t hv[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = i0 + k;
-                            const uint32_t in8 = cb[i];
-                            const uint32_t out8 = i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8;
-                            const uint2 tt = xy_at(S, out8, in8);
-                            fh = rol1<W31>(fh) ^ tt.x;
-                            rh = ror1<W31>(rh) ^ tt.y;
-                            hv[k] = min(fh, rh);
-                        }
-                        if (min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= A.thr) {   // rare: ~8 % of groups at d=0.01
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (hv[k] <= A.thr) { mask |= 1ull << (i0 + k); hs[v0 + i0 + k] = hv[k]; }
-                        }
+                        for (int k = 0; k < 4; ++k)
+                            if (hv[k] <= A.thr) { mask[(i0 + k) >> 6] |= 1ull << ((i0 + k) & 63); hs[v0 + i0 + k] = hv[k]; }
                     }
-                    mask &= ~invalid & lowmask64((uint32_t)n_u);     // owners >= n_u hashed garbage
                 }
+#pragma unroll
+                for (int x = 0; x < MW; ++x)                       // owners >= n_u hashed garbage
+                    mask[x] &= ~invalid[x] & lowmask64((uint32_t)max(min(n_u - 64 * x, 64), 0));
             }
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int x = 0; x < MW; ++x) cnt += __popcll(mask[x]);
             uint32_t tot;
-            const uint32_t ex = block_excl_scan(__popcll(mask), S.wsum, tot);
-            S.hitw[pass][tid] = mask;
+            const uint32_t ex = block_excl_scan(cnt, S.wsum, tot);
+#pragma unroll
+            for (int x = 0; x < MW; ++x) S.hitw[pass][tid][x] = mask[x];
             S.hitpre[pass][tid] = tile_min + ex;
             tile_min += tot;
-            if (tid == NT - 1) { S.hitw[pass][NT] = 0ull; S.hitpre[pass][NT] = tile_min; }
+            if (tid == NT - 1) {
+#pragma unroll
+                for (int x = 0; x < MW; ++x) S.hitw[pass][NT][x] = 0ull;
+                S.hitpre[pass][NT] = tile_min;
+            }
         }
 
         // ---- S6b: claim a contiguous run of records for this tile (tiles land in any order; k_finalize sorts them out)
@@ -507,13 +539,16 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             if (base) __syncthreads();                     // previous round has been consumed
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
-                unsigned long long m = S.hitw[pass][tid];
                 uint32_t o = S.hitpre[pass][tid];
-                while (m) {
-                    const int i = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    if (o >= base && o < base + HL) S.hl[o - base] = (uint16_t)(pass * CAP + CH * tid + i);
-                    ++o;
+#pragma unroll
+                for (int x = 0; x < MW; ++x) {
+                    unsigned long long m = S.hitw[pass][tid][x];
+                    while (m) {
+                        const int i = __ffsll((long long)m) - 1 + 64 * x;
+                        m &= m - 1;
+                        if (o >= base && o < base + HL) S.hl[o - base] = (uint16_t)(pass * CAP + CH * tid + i);
+                        ++o;
+                    }
                 }
             }
             __syncthreads();
@@ -549,7 +584,10 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             const uint32_t v = qx - hk;
             const uint32_t pass = v >= (uint32_t)CAP ? 1u : 0u;
             const uint32_t vv = v - pass * CAP, u = vv / CH, bit = vv - u * CH;
-            const uint32_t hb = S.hitpre[pass][u] + __popcll(S.hitw[pass][u] & lowmask64(bit));
+            uint32_t hb = S.hitpre[pass][u];
+#pragma unroll
+            for (int x = 0; x < MW; ++x)
+                hb += __popcll(S.hitw[pass][u][x] & lowmask64((uint32_t)max(min((int)bit - 64 * x, 64), 0)));
             A.min_off[i] = hb;
             if (A.hpc_off) A.hpc_off[i] = v;
         }
@@ -557,62 +595,107 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ tile order
-// Exclusive prefix over tiles of (hits, kept bases): one CTA, each thread owns a contiguous run of tiles.
-constexpr int ST = 1024;
-__global__ void __launch_bounds__(ST) k_tile_scan(const uint4 *__restrict__ tile_info, uint32_t n_tiles,
-                                                  ulonglong2 *__restrict__ tile_base)
+// k_minimizers leaves each tile's records contiguous but the tiles in completion order.  k_finalize restores the
+// order: per chunk of 256 tiles an exclusive block scan of (hits, kept bases), a decoupled look-back across chunks
+// (two status arrays, walked by two warps), then one warp per tile copies the records to their final place and turns
+// the tile-local per-sequence prefixes into global ones.
+__device__ __forceinline__ uint64_t lookback_excl(uint64_t *status, uint32_t c, uint64_t agg, uint32_t *err, int lane)
 {
-    S2K_SHARED unsigned long long sm[ST], sk[ST];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t per = (n_tiles + ST - 1) / ST;
-    const uint32_t b = min(tid * per, n_tiles), e = min(b + per, n_tiles);
-    unsigned long long m = 0, k = 0;
-    for (uint32_t t = b; t < e; ++t) { const uint4 x = tile_info[t]; m += x.x; k += x.y; }
-    sm[tid] = m; sk[tid] = k;
-    __syncthreads();
-    for (uint32_t o = 1; o < ST; o <<= 1) {
-        unsigned long long am = 0, ak = 0;
-        if (tid >= o) { am = sm[tid - o]; ak = sk[tid - o]; }
-        __syncthreads();
-        sm[tid] += am; sk[tid] += ak;
-        __syncthreads();
+    uint64_t excl = 0;
+    if (c > 0) {
+        if (lane == 0) st_relaxed(&status[c], FLAG_AGG | agg);
+        int64_t j = (int64_t)c - 1;
+        for (;;) {
+            const int64_t idx = j - lane;
+            uint64_t s = FLAG_INCL;
+            if (idx >= 0) {
+                uint32_t spins = 0;
+                while (((s = ld_relaxed(&status[idx])) >> 62) == 0) {
+                    if (++spins > SPIN_LIMIT) { atomicOr(err, ERR_SPIN); s = FLAG_INCL; break; }
+                    __nanosleep(40);
+                }
+            }
+            const uint32_t im = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+            const int first = im ? (__ffs(im) - 1) : 32;
+            excl += warp_sum64(lane <= first ? (s & VALMASK) : 0ull);
+            if (im) break;
+            j -= 32;
+        }
     }
-    unsigned long long pm = sm[tid] - m, pk = sk[tid] - k;
-    for (uint32_t t = b; t < e; ++t) {
-        const uint4 x = tile_info[t];
-        tile_base[t] = make_ulonglong2(pm, pk);
-        pm += x.x; pk += x.y;
-    }
-    if (tid == ST - 1) tile_base[n_tiles] = make_ulonglong2(sm[ST - 1], sk[ST - 1]);
+    if (lane == 0) st_relaxed(&status[c], FLAG_INCL | (excl + agg));
+    return excl;
 }
 
-// One warp per tile: move the tile's records to their final, ordered place and turn the tile-local
-// per-sequence offsets into global ones.
+constexpr int FT = 256;            // tiles per chunk == threads per CTA
 struct KFArgs {
     const uint4 *tile_info;
-    const ulonglong2 *tile_base;
     const uint32_t *tile_lb;
     const uint4 *tmp;
     uint4 *mins;
     uint64_t *min_off, *hpc_off;
+    uint64_t *status_a, *status_b;   // per chunk, zeroed
+    uint32_t *ticket, *err;
     uint64_t n_seqs, n_bases, min_cap;
     uint32_t n_tiles, tile;
 };
-__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs A)
+__global__ void __launch_bounds__(FT) k_finalize(const __grid_constant__ KFArgs A)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < A.n_tiles; t += nwarps) {
-        const uint4 info = A.tile_info[t];
-        const ulonglong2 base = A.tile_base[t];
-        const uint64_t src = ((uint64_t)info.w << 32) | info.z;
-        if (src + info.x <= A.min_cap)
-            for (uint32_t j = lane; j < info.x; j += 32) A.mins[base.x + j] = A.tmp[src + j];
-        const bool last_tile = (uint64_t)(t + 1) * A.tile >= A.n_bases;
-        const uint32_t lb = A.tile_lb[t], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
-        for (uint32_t i = lb + lane; i < ub; i += 32) {
-            A.min_off[i] += base.x;
-            if (A.hpc_off) A.hpc_off[i] += base.y;
+    S2K_SHARED unsigned long long wsum64[FT / 32];
+    S2K_SHARED unsigned long long s_base[2];
+    S2K_SHARED uint32_t s_chunk;
+    S2K_SHARED uint4 s_info[FT];
+    S2K_SHARED unsigned long long s_bm[FT], s_bk[FT];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_chunks = (A.n_tiles + FT - 1) / FT;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_chunk = atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        const uint32_t c = s_chunk;
+        if (c >= n_chunks) break;
+        const uint32_t t = c * FT + tid;
+        uint4 info = make_uint4(0, 0, 0, 0);
+        if (t < A.n_tiles) info = A.tile_info[t];
+        // exclusive scan of (hits | kept << 32) inside the chunk: per-chunk sums stay below 2^32
+        const unsigned long long v = (unsigned long long)info.x | ((unsigned long long)info.y << 32);
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += x;
+        }
+        if (lane == 31) wsum64[warp] = incl;
+        __syncthreads();
+        unsigned long long pre = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < FT / 32; ++i) { const unsigned long long x = wsum64[i]; if (i < (int)warp) pre += x; tot += x; }
+        const unsigned long long ex = pre + incl - v;
+        if (warp == 0) {
+            const uint64_t e = lookback_excl(A.status_a, c, tot & 0xffffffffull, A.err, (int)lane);
+            if (lane == 0) s_base[0] = e;
+        } else if (warp == 1) {
+            const uint64_t e = lookback_excl(A.status_b, c, tot >> 32, A.err, (int)lane);
+            if (lane == 0) s_base[1] = e;
+        }
+        __syncthreads();
+        s_info[tid] = info;
+        s_bm[tid] = s_base[0] + (ex & 0xffffffffull);
+        s_bk[tid] = s_base[1] + (ex >> 32);
+        __syncthreads();
+        for (uint32_t j = warp; j < FT; j += FT / 32) {     // one warp per tile
+            const uint32_t tt = c * FT + j;
+            if (tt >= A.n_tiles) break;
+            const uint4 inf = s_info[j];
+            const uint64_t bm = s_bm[j], bk = s_bk[j];
+            const uint64_t src = ((uint64_t)inf.w << 32) | inf.z;
+            if (src + inf.x <= A.min_cap)
+                for (uint32_t r = lane; r < inf.x; r += 32) A.mins[bm + r] = A.tmp[src + r];
+            const bool last_tile = (uint64_t)(tt + 1) * A.tile >= A.n_bases;
+            const uint32_t lb = A.tile_lb[tt], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[tt + 1];
+            for (uint32_t i = lb + lane; i < ub; i += 32) {
+                A.min_off[i] += bm;
+                if (A.hpc_off) A.hpc_off[i] += bk;
+            }
         }
     }
 }
@@ -758,23 +841,55 @@ __device__ __forceinline__ uint64_t rol64(uint64_t x, uint32_t r)
     r &= 63u;
     return r ? ((x << r) | (x >> (64u - r))) : x;
 }
-__global__ void __launch_bounds__(256) k_windows(const __grid_constant__ K3Args A)
+// One thread per minimizer = per candidate window start.  A CTA stages its 256 records plus the k-1 that follow
+// (mixed once, not k times) in shared memory; windows longer than the staging area take the direct path.
+constexpr int WT = 256, WK_MAX = 64;
+__global__ void __launch_bounds__(WT) k_windows(const __grid_constant__ K3Args A)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_min; g += stride) {
-        const uint4 first = A.mins[g];
+    S2K_SHARED unsigned long long sm[WT + WK_MAX];
+    S2K_SHARED uint32_t send[WT + WK_MAX];
+    const uint32_t tid = threadIdx.x, k = A.k;
+    const uint64_t n_chunks = (A.n_min + WT - 1) / WT;
+    const bool staged = k - 1 <= (uint32_t)WK_MAX;
+    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const uint64_t g0 = chunk * WT, g = g0 + tid;
+        const uint32_t n_load = (uint32_t)min((uint64_t)(WT + k - 1), A.n_min - g0);
+        uint4 first = make_uint4(0, 0, 0, 0);
+        if (staged) {
+            __syncthreads();
+            for (uint32_t i = tid; i < n_load; i += WT) {
+                const uint4 r = A.mins[g0 + i];
+                if (i == tid) first = r;
+                sm[i] = mix32(r.x);
+                send[i] = r.z;
+            }
+            __syncthreads();
+        } else if (g < A.n_min) {
+            first = A.mins[g];
+        }
+        if (g >= A.n_min) continue;
         const uint32_t rid = first.w;
         const uint64_t c = g - A.min_off[rid];             // window index inside the sequence == offset
         const uint64_t k0 = A.km_off[rid];
         if (c >= A.km_off[rid + 1] - k0) continue;         // fewer than k minimizers left (or tail rule)
         uint64_t f = 0, r = 0;
-        uint32_t end = first.z;
-        for (uint32_t tt = 0; tt < A.k; ++tt) {
-            const uint4 mrec = tt ? A.mins[g + tt] : first;
-            const uint64_t m = mix32(mrec.x);
-            f ^= rol64(m, A.k - 1 - tt);
-            r ^= rol64(m, tt);
-            end = mrec.z;
+        uint32_t end;
+        if (staged) {
+            for (uint32_t tt = 0; tt < k; ++tt) {
+                const uint64_t m = sm[tid + tt];
+                f ^= rol64(m, k - 1 - tt);
+                r ^= rol64(m, tt);
+            }
+            end = send[tid + k - 1];
+        } else {
+            end = first.z;
+            for (uint32_t tt = 0; tt < k; ++tt) {
+                const uint4 mrec = tt ? A.mins[g + tt] : first;
+                const uint64_t m = mix32(mrec.x);
+                f ^= rol64(m, k - 1 - tt);
+                r ^= rol64(m, tt);
+                end = mrec.z;
+            }
         }
         const uint64_t o = k0 + c;
         A.hash[o] = f < r ? f : r;
@@ -901,6 +1016,13 @@ __global__ void k_add_u64(uint64_t *__restrict__ a, uint64_t n, uint64_t add)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] += add;
 }
+__global__ void k_sub_first(uint64_t *__restrict__ a, uint64_t n)     // a[i] -= a[0], a[0] last
+{
+    const uint64_t base = a[0];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = 1 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] -= base;
+}
+__global__ void k_zero_first(uint64_t *a) { a[0] = 0; }
 __global__ void k_add_seq(uint4 *__restrict__ mins, uint64_t n, uint32_t add)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
