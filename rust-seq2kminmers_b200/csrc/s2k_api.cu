@@ -339,21 +339,24 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     }
     if ((rc = ensure(ctx, ctx->d_mins, std::max<uint64_t>(n_min, 1) * sizeof(uint4), false))) return rc;
     {
-        const uint32_t n_chunks = (n_tiles + FT - 1) / FT;
-        if ((rc = ensure(ctx, ctx->d_tile_base, (uint64_t)n_chunks * 16 + 16, false))) return rc;
+        const uint32_t n_chunks = (n_tiles + ST - 1) / ST;
+        // d_tile_base: [tile_loc u64 x n_tiles][chunk_tot u64 x n_chunks][chunk_base u64x2 x (n_chunks+1)]
+        if ((rc = ensure(ctx, ctx->d_tile_base, ((uint64_t)n_tiles + n_chunks + 2) * 8 + ((uint64_t)n_chunks + 1) * 16 + 16, false))) return rc;
+        unsigned long long *tile_loc = ptr<unsigned long long>(ctx->d_tile_base);
+        unsigned long long *chunk_tot = tile_loc + n_tiles;
+        ulonglong2 *chunk_base = reinterpret_cast<ulonglong2 *>(
+            (reinterpret_cast<uintptr_t>(chunk_tot + n_chunks) + 15) & ~uintptr_t(15));
+        S2K_LAUNCH(k_tile_scan_a, n_chunks, ST, 0, st, false, ptr<uint4>(ctx->d_tile_info), n_tiles, tile_loc, chunk_tot);
+        S2K_LAUNCH(k_tile_scan_b, 1, ST, 0, st, false, chunk_tot, n_chunks, chunk_base);
         KFArgs F;
-        F.tile_info = ptr<uint4>(ctx->d_tile_info);
+        F.tile_info = ptr<uint4>(ctx->d_tile_info); F.tile_loc = tile_loc; F.chunk_base = chunk_base;
         F.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
         F.min_off = ptr<uint64_t>(ctx->d_min_off); F.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
-        F.status_a = ptr<uint64_t>(ctx->d_tile_base); F.status_b = F.status_a + n_chunks;
-        F.ticket = reinterpret_cast<uint32_t *>(small + 6); F.err = reinterpret_cast<uint32_t *>(small + 5);
         F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = cap; F.n_tiles = n_tiles; F.tile = P.tile;
-        CU(cudaMemsetAsync(F.status_a, 0, (uint64_t)n_chunks * 16, st));
-        CU(cudaMemsetAsync(F.ticket, 0, 4, st));
-        const int gridf = (int)std::min<uint64_t>(n_chunks, (uint64_t)ctx->sm_count * 4);
-        S2K_LAUNCH(k_finalize, gridf, FT, 0, st, false, F);
+        const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 8);
+        S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
         CU(cudaGetLastError());
-        ctx->launches += 1;
+        ctx->launches += 3;
     }
     ctx->rate_hint = std::max(ctx->rate_hint, (double)n_min / (double)n_bases);
 
@@ -388,7 +391,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);
         C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
         if (n_min > 0) {
-            const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 16);
             S2K_LAUNCH(k_windows, g3, 256, 0, st, false, C);
             CU(cudaGetLastError());
             ctx->launches += 1;

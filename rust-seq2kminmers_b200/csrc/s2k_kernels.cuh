@@ -595,107 +595,90 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ tile order
-// k_minimizers leaves each tile's records contiguous but the tiles in completion order.  k_finalize restores the
-// order: per chunk of 256 tiles an exclusive block scan of (hits, kept bases), a decoupled look-back across chunks
-// (two status arrays, walked by two warps), then one warp per tile copies the records to their final place and turns
-// the tile-local per-sequence prefixes into global ones.
-__device__ __forceinline__ uint64_t lookback_excl(uint64_t *status, uint32_t c, uint64_t agg, uint32_t *err, int lane)
+// k_minimizers leaves each tile's records contiguous but the tiles in completion order.  Two-level exclusive prefix
+// of the per-tile (hits, kept bases): k_tile_scan_a = one thread per tile, block scan over 1024 tiles;
+// k_tile_scan_b = one CTA over the chunk totals.  k_finalize = one warp per tile: copy the records to their final,
+// ordered place and turn the tile-local per-sequence prefixes into global ones.
+constexpr int ST = 1024;
+__global__ void __launch_bounds__(ST) k_tile_scan_a(const uint4 *__restrict__ tile_info, uint32_t n_tiles,
+                                                    unsigned long long *__restrict__ tile_loc,
+                                                    unsigned long long *__restrict__ chunk_tot)
 {
-    uint64_t excl = 0;
-    if (c > 0) {
-        if (lane == 0) st_relaxed(&status[c], FLAG_AGG | agg);
-        int64_t j = (int64_t)c - 1;
-        for (;;) {
-            const int64_t idx = j - lane;
-            uint64_t s = FLAG_INCL;
-            if (idx >= 0) {
-                uint32_t spins = 0;
-                while (((s = ld_relaxed(&status[idx])) >> 62) == 0) {
-                    if (++spins > SPIN_LIMIT) { atomicOr(err, ERR_SPIN); s = FLAG_INCL; break; }
-                    __nanosleep(40);
-                }
-            }
-            const uint32_t im = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-            const int first = im ? (__ffs(im) - 1) : 32;
-            excl += warp_sum64(lane <= first ? (s & VALMASK) : 0ull);
-            if (im) break;
-            j -= 32;
-        }
+    S2K_SHARED unsigned long long ws[ST / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t t = blockIdx.x * ST + tid;
+    unsigned long long v = 0;                              // hits | kept << 32: a chunk's sums stay below 2^32
+    if (t < n_tiles) { const uint4 x = tile_info[t]; v = (unsigned long long)x.x | ((unsigned long long)x.y << 32); }
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += y;
     }
-    if (lane == 0) st_relaxed(&status[c], FLAG_INCL | (excl + agg));
-    return excl;
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    unsigned long long pre = 0, tot = 0;
+    for (int i = 0; i < ST / 32; ++i) { const unsigned long long y = ws[i]; if (i < (int)warp) pre += y; tot += y; }
+    if (t < n_tiles) tile_loc[t] = pre + incl - v;
+    if (tid == 0) chunk_tot[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(ST) k_tile_scan_b(const unsigned long long *__restrict__ chunk_tot, uint32_t n_chunks,
+                                                    ulonglong2 *__restrict__ chunk_base)
+{
+    S2K_SHARED unsigned long long sa[ST], sb[ST];
+    S2K_SHARED unsigned long long carry[2];
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { carry[0] = 0; carry[1] = 0; }
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += ST) {
+        __syncthreads();
+        const uint32_t c = c0 + tid;
+        const unsigned long long v = c < n_chunks ? chunk_tot[c] : 0ull;
+        const unsigned long long a = v & 0xffffffffull, b = v >> 32;
+        sa[tid] = a; sb[tid] = b;
+        __syncthreads();
+        for (uint32_t o = 1; o < ST; o <<= 1) {
+            unsigned long long xa = 0, xb = 0;
+            if (tid >= o) { xa = sa[tid - o]; xb = sb[tid - o]; }
+            __syncthreads();
+            sa[tid] += xa; sb[tid] += xb;
+            __syncthreads();
+        }
+        if (c < n_chunks) chunk_base[c] = make_ulonglong2(carry[0] + sa[tid] - a, carry[1] + sb[tid] - b);
+        __syncthreads();
+        if (tid == ST - 1) { carry[0] += sa[tid]; carry[1] += sb[tid]; }
+    }
+    __syncthreads();
+    if (tid == 0) chunk_base[n_chunks] = make_ulonglong2(carry[0], carry[1]);
 }
 
-constexpr int FT = 256;            // tiles per chunk == threads per CTA
 struct KFArgs {
     const uint4 *tile_info;
+    const unsigned long long *tile_loc;
+    const ulonglong2 *chunk_base;
     const uint32_t *tile_lb;
     const uint4 *tmp;
     uint4 *mins;
     uint64_t *min_off, *hpc_off;
-    uint64_t *status_a, *status_b;   // per chunk, zeroed
-    uint32_t *ticket, *err;
     uint64_t n_seqs, n_bases, min_cap;
     uint32_t n_tiles, tile;
 };
-__global__ void __launch_bounds__(FT) k_finalize(const __grid_constant__ KFArgs A)
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs A)
 {
-    S2K_SHARED unsigned long long wsum64[FT / 32];
-    S2K_SHARED unsigned long long s_base[2];
-    S2K_SHARED uint32_t s_chunk;
-    S2K_SHARED uint4 s_info[FT];
-    S2K_SHARED unsigned long long s_bm[FT], s_bk[FT];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_chunks = (A.n_tiles + FT - 1) / FT;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_chunk = atomicAdd(A.ticket, 1u);
-        __syncthreads();
-        const uint32_t c = s_chunk;
-        if (c >= n_chunks) break;
-        const uint32_t t = c * FT + tid;
-        uint4 info = make_uint4(0, 0, 0, 0);
-        if (t < A.n_tiles) info = A.tile_info[t];
-        // exclusive scan of (hits | kept << 32) inside the chunk: per-chunk sums stay below 2^32
-        const unsigned long long v = (unsigned long long)info.x | ((unsigned long long)info.y << 32);
-        unsigned long long incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += x;
-        }
-        if (lane == 31) wsum64[warp] = incl;
-        __syncthreads();
-        unsigned long long pre = 0, tot = 0;
-#pragma unroll
-        for (int i = 0; i < FT / 32; ++i) { const unsigned long long x = wsum64[i]; if (i < (int)warp) pre += x; tot += x; }
-        const unsigned long long ex = pre + incl - v;
-        if (warp == 0) {
-            const uint64_t e = lookback_excl(A.status_a, c, tot & 0xffffffffull, A.err, (int)lane);
-            if (lane == 0) s_base[0] = e;
-        } else if (warp == 1) {
-            const uint64_t e = lookback_excl(A.status_b, c, tot >> 32, A.err, (int)lane);
-            if (lane == 0) s_base[1] = e;
-        }
-        __syncthreads();
-        s_info[tid] = info;
-        s_bm[tid] = s_base[0] + (ex & 0xffffffffull);
-        s_bk[tid] = s_base[1] + (ex >> 32);
-        __syncthreads();
-        for (uint32_t j = warp; j < FT; j += FT / 32) {     // one warp per tile
-            const uint32_t tt = c * FT + j;
-            if (tt >= A.n_tiles) break;
-            const uint4 inf = s_info[j];
-            const uint64_t bm = s_bm[j], bk = s_bk[j];
-            const uint64_t src = ((uint64_t)inf.w << 32) | inf.z;
-            if (src + inf.x <= A.min_cap)
-                for (uint32_t r = lane; r < inf.x; r += 32) A.mins[bm + r] = A.tmp[src + r];
-            const bool last_tile = (uint64_t)(tt + 1) * A.tile >= A.n_bases;
-            const uint32_t lb = A.tile_lb[tt], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[tt + 1];
-            for (uint32_t i = lb + lane; i < ub; i += 32) {
-                A.min_off[i] += bm;
-                if (A.hpc_off) A.hpc_off[i] += bk;
-            }
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < A.n_tiles; t += nwarps) {
+        const uint4 info = A.tile_info[t];
+        const ulonglong2 cb = A.chunk_base[t / ST];
+        const unsigned long long loc = A.tile_loc[t];
+        const uint64_t bm = cb.x + (loc & 0xffffffffull), bk = cb.y + (loc >> 32);
+        const uint64_t src = ((uint64_t)info.w << 32) | info.z;
+        if (src + info.x <= A.min_cap)
+            for (uint32_t j = lane; j < info.x; j += 32) A.mins[bm + j] = A.tmp[src + j];
+        const bool last_tile = (uint64_t)(t + 1) * A.tile >= A.n_bases;
+        const uint32_t lb = A.tile_lb[t], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
+        for (uint32_t i = lb + lane; i < ub; i += 32) {
+            A.min_off[i] += bm;
+            if (A.hpc_off) A.hpc_off[i] += bk;
         }
     }
 }
@@ -841,55 +824,23 @@ __device__ __forceinline__ uint64_t rol64(uint64_t x, uint32_t r)
     r &= 63u;
     return r ? ((x << r) | (x >> (64u - r))) : x;
 }
-// One thread per minimizer = per candidate window start.  A CTA stages its 256 records plus the k-1 that follow
-// (mixed once, not k times) in shared memory; windows longer than the staging area take the direct path.
-constexpr int WT = 256, WK_MAX = 64;
-__global__ void __launch_bounds__(WT) k_windows(const __grid_constant__ K3Args A)
+__global__ void __launch_bounds__(256) k_windows(const __grid_constant__ K3Args A)
 {
-    S2K_SHARED unsigned long long sm[WT + WK_MAX];
-    S2K_SHARED uint32_t send[WT + WK_MAX];
-    const uint32_t tid = threadIdx.x, k = A.k;
-    const uint64_t n_chunks = (A.n_min + WT - 1) / WT;
-    const bool staged = k - 1 <= (uint32_t)WK_MAX;
-    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const uint64_t g0 = chunk * WT, g = g0 + tid;
-        const uint32_t n_load = (uint32_t)min((uint64_t)(WT + k - 1), A.n_min - g0);
-        uint4 first = make_uint4(0, 0, 0, 0);
-        if (staged) {
-            __syncthreads();
-            for (uint32_t i = tid; i < n_load; i += WT) {
-                const uint4 r = A.mins[g0 + i];
-                if (i == tid) first = r;
-                sm[i] = mix32(r.x);
-                send[i] = r.z;
-            }
-            __syncthreads();
-        } else if (g < A.n_min) {
-            first = A.mins[g];
-        }
-        if (g >= A.n_min) continue;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_min; g += stride) {
+        const uint4 first = A.mins[g];
         const uint32_t rid = first.w;
         const uint64_t c = g - A.min_off[rid];             // window index inside the sequence == offset
         const uint64_t k0 = A.km_off[rid];
         if (c >= A.km_off[rid + 1] - k0) continue;         // fewer than k minimizers left (or tail rule)
         uint64_t f = 0, r = 0;
-        uint32_t end;
-        if (staged) {
-            for (uint32_t tt = 0; tt < k; ++tt) {
-                const uint64_t m = sm[tid + tt];
-                f ^= rol64(m, k - 1 - tt);
-                r ^= rol64(m, tt);
-            }
-            end = send[tid + k - 1];
-        } else {
-            end = first.z;
-            for (uint32_t tt = 0; tt < k; ++tt) {
-                const uint4 mrec = tt ? A.mins[g + tt] : first;
-                const uint64_t m = mix32(mrec.x);
-                f ^= rol64(m, k - 1 - tt);
-                r ^= rol64(m, tt);
-                end = mrec.z;
-            }
+        uint32_t end = first.z;
+        for (uint32_t tt = 0; tt < A.k; ++tt) {
+            const uint4 mrec = tt ? A.mins[g + tt] : first;
+            const uint64_t m = mix32(mrec.x);
+            f ^= rol64(m, A.k - 1 - tt);
+            r ^= rol64(m, tt);
+            end = mrec.z;
         }
         const uint64_t o = k0 + c;
         A.hash[o] = f < r ? f : r;
