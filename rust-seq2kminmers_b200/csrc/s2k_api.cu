@@ -15,6 +15,10 @@
 
 using namespace s2k;
 
+#ifndef S2K_WARP
+#define S2K_WARP 0                  // 1: k_minimizers_w (warp-independent sub-tiles), 0: k_minimizers
+#endif
+
 // Kernel launch.  `conc` only matters to the test-tier host emulation (tests/emu): kernels with static shared
 // state run their blocks one after the other there.
 #ifdef S2K_EMU
@@ -183,8 +187,14 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     P.d = (p->mode == S2K_MODE_HPC) ? 1u : 0u;       // Hpc: the l-mer is emitted when the NEXT kept base shows up
     P.need = P.l - 1 + P.d;
     P.quirk = P.simd && !P.w31;
+#if S2K_WARP
+    // warp-tile kernel: per-warp halo of 64 raw bases when that almost surely holds l-1(+1) kept bases, else 256
+    P.halo = (P.hpc ? P.need <= 31 : P.need <= 64) ? 64u : 256u;
+    P.tile = (uint32_t)WTILE;
+#else
     P.halo = P.need >= 128 ? 512u : 256u;
     P.tile = P.hpc ? (uint32_t)WIN - P.halo : std::min<uint32_t>((uint32_t)CAP, (uint32_t)WIN - P.halo);
+#endif
     const uint32_t bs = bound_scalar(p->density);
     uint64_t excl;                                   // select iff hash < excl
     if (P.simd) { uint32_t b = bound_simd(bs); if (P.w31) b /= 2; excl = b; }
@@ -229,6 +239,10 @@ int set_attrs(s2k_ctx *ctx)
     CU(cudaFuncSetAttribute(k_minimizers<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_minimizers<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_minimizers<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_minimizers_w<false, false, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<68>)));
+    CU(cudaFuncSetAttribute(k_minimizers_w<false, true, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<68>)));
+    CU(cudaFuncSetAttribute(k_minimizers_w<true, false, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<52>)));
+    CU(cudaFuncSetAttribute(k_minimizers_w<true, true, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<52>)));
     ctx->attr_set = true;
     return S2K_OK;
 }
@@ -282,10 +296,16 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     const uint64_t n_tiles64 = (n_bases + P.tile - 1) / P.tile;
     if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
     const uint32_t n_tiles = (uint32_t)n_tiles64;
+#if S2K_WARP
+    const int max_grid = ctx->sm_count * 3;
+    const size_t hscr_words = (size_t)max_grid * 8 * HSW;
+#else
     const int max_grid = ctx->sm_count * S2K_MINB;
+    const size_t hscr_words = (size_t)max_grid * WIN;
+#endif
     if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_hscr, (size_t)max_grid * WIN * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_status, ((n_seqs + RT * RPT - 1) / (RT * RPT)) * 8 + 8, false))) return rc;
 
     // capacity of the minimizer stream: expected 2*density*(kept bases), with head room; grown and rerun on overflow
@@ -319,12 +339,18 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.min_out = ptr<uint4>(ctx->d_tmp); A.min_cap = cap;
         CU(cudaMemsetAsync(small, 0, 64, st));
         const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
-        const size_t smem = sizeof(Smem);
         Timing &T = ctx->tm;
         const bool rec = T.enabled && T.n < 64;
         if (rec) cudaEventRecord(T.ev[T.n][0], st);
+#if S2K_WARP
+        const size_t smem = P.hpc ? sizeof(SmemW<52>) : sizeof(SmemW<68>);
+        void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers_w<true, true, 52> : k_minimizers_w<true, false, 52>)
+                                          : (P.w31 ? k_minimizers_w<false, true, 68> : k_minimizers_w<false, false, 68>);
+#else
+        const size_t smem = sizeof(Smem);
         void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
                                           : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
+#endif
         S2K_LAUNCH(kfn, grid, NT, smem, st, true, A);
         if (rec) { cudaEventRecord(T.ev[T.n][1], st); ++T.n; }
         CU(cudaGetLastError());

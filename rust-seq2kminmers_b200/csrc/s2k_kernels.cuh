@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 unsigned long long invalid[MW];
 #pragma unroll
                 for (int x = 0; x < MW; ++x) invalid[x] = 0ull;
-                {
+                if (S.n_dirty[par] != 0) {                         // uniform: no flag was set in this tile -> nothing to mask
                     const int L1 = l - 1 + d, o0 = v0 + XB;
                     const int w_hi = (o0 + CH - 1) >> 5, w_lo = (o0 - L1 - 1) >> 5;
                     for (int wi = w_lo; wi <= w_hi; ++wi) {
@@ -593,6 +593,10 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         }
     }
 }
+
+} // namespace s2k
+#include "s2k_kernel_warp.cuh"
+namespace s2k {
 
 // ------------------------------------------------------------------------------------------------ tile order
 // k_minimizers leaves each tile's records contiguous but the tiles in completion order.  Two-level exclusive prefix

@@ -112,6 +112,11 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int o)
     const int lane = (int)(threadIdx.x & 31);
     return emu_warp_exchange(v, lane ^ o, true);
 }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src)
+{
+    return emu_warp_exchange(v, src & 31, true);
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::blk->wbar[threadIdx.x >> 5]->arrive_and_wait(); }
 static inline unsigned __ballot_sync(unsigned, bool pred)
 {
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
