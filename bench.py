@@ -186,17 +186,26 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = S.Context(local_rank)
     ctx.set_timing(True)
-    n_bases = L * n_reads
-    first_read = rank * n_reads                      # each rank owns its own slice of the synthetic stream
+    split_one = args.workload == "c4" and world > 1    # one sequence cut into base ranges: strong scaling
+    sharding = importlib.import_module("rust-seq2kminmers_b200.sharding")
+    if split_one:
+        b0, b1, lo, hi = sharding.sequence_ranges(L, world, sharding.default_overlap_right(L_PARAM, K_PARAM, DENSITY))[rank]
+        n_bases, first_base = hi - lo, lo
+        config["sharding"] = f"one sequence cut into {world} base ranges, overlap-and-trim by ownership, no exchange of bases"
+    else:
+        n_bases, first_base = L * n_reads, rank * n_reads * L   # each rank owns its own slice of the synthetic stream
     d_bases = torch.empty(n_bases + 16, dtype=torch.uint8, device=dev)
-    ctx.synth_device(seed, first_read * L, n_bases, d_bases.data_ptr())
-    d_so = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
+    ctx.synth_device(seed, first_base, n_bases, d_bases.data_ptr())
+    if split_one:
+        d_so = torch.tensor([0, n_bases], dtype=torch.int64, device=dev)
+    else:
+        d_so = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         return ctx.run_device(d_bases.data_ptr(), d_so.data_ptr(), n_reads, n_bases, L_PARAM, K_PARAM, DENSITY,
-                              S.HashMode(mode), S.HashVariant(variant), stream=stream)
+                              S.HashMode(mode), S.HashVariant(variant), stream=stream, no_tail_rule=split_one)
 
     def barrier():
         if world > 1:
@@ -206,6 +215,12 @@ def main():
     for _ in range(max(args.warmup, 3)):
         res = step()
     n_items, n_min = int(res.n_items), int(res.n_minimizers)
+    if split_one:                                      # what this rank OWNS: windows whose first minimizer starts in [b0, b1)
+        mins_t = torch.as_tensor(S.DeviceArray(res.minimizers, n_min * 16, "|u1"), device=dev).view(torch.int32).view(-1, 4)
+        starts = (mins_t[:, 1].to(torch.int64) & 0xffffffff) + lo
+        i0 = int(torch.searchsorted(starts, torch.tensor([b0], device=dev))[0])
+        i1 = n_min if rank == world - 1 else int(torch.searchsorted(starts, torch.tensor([b1], device=dev))[0])
+        n_items, n_min = max(0, min(i1, max(0, n_min - K_PARAM + 1)) - i0), i1 - i0
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -226,11 +241,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    value = world * n_bases / (ms_step * 1e-3) / 1e9
+    value = (L if split_one else world * n_bases) / (ms_step * 1e-3) / 1e9
 
     # optional final gather of per-GPU counts over NCCL (the only collective; not on the data path)
     if world > 1:
-        sharding = importlib.import_module("rust-seq2kminmers_b200.sharding")
         per_rank, _first_item = sharding.gather_totals(n_items, n_min, device=dev)
         counts = torch.tensor(per_rank.sum(axis=0))
     else:
@@ -268,8 +282,8 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        assert out.n_items == n_items
-        e2e = {"value": world * n_bases * e_steps / float(tt.item()) / 1e9, "unit": "Gbp/s",
+        assert split_one or out.n_items == n_items
+        e2e = {"value": (L if split_one else world * n_bases) * e_steps / float(tt.item()) / 1e9, "unit": "Gbp/s",
                "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
                "d2h_bytes_per_step": 17 * n_items + 8 * (n_reads + 1) * 2 + 4 * n_reads,
                "steps": e_steps, "api": "s2k_run (C ABI, pinned host buffers)"}
@@ -284,7 +298,8 @@ def main():
 
     if rank == 0:
         line = {"metric": "input Gbp/s -> k-min-mers", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if split_one else "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "items_per_step": int(counts[0].item()), "minimizers_per_step": int(counts[1].item())}

@@ -107,6 +107,9 @@ typedef struct s2k_ctx s2k_ctx;
 
 /* Flags for s2k_ctx_set_flags. */
 #define S2K_WANT_MINIMIZERS 1u  /* s2k_run (host) also copies the minimizer stream back */
+#define S2K_NO_TAIL_RULE    2u  /* do not apply the `(len-l+1) % 16 == 0` tail rule of src/nthash_avx512_32.rs:134-138:
+                                   for callers that process one sequence in pieces (sharding.py) and apply the rule
+                                   themselves from the length of the whole sequence */
 
 /* Lifetime.  One context = one CUDA device + one stream + grow-only device/pinned buffers.
  * A context is single-threaded (like one KminmersIterator, src/main.rs:65-79); distinct contexts may be

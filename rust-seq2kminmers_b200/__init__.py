@@ -259,7 +259,8 @@ class Context:
 
     # -- host buffers in, host (pinned) results out ------------------------------------------------------
     def run(self, bases, seq_off, l: int, k: int, density: float, mode: HashMode,
-            variant: HashVariant = HashVariant.NT1_32, want_minimizers: bool = False, copy: bool = True) -> KminmersBatch:
+            variant: HashVariant = HashVariant.NT1_32, want_minimizers: bool = False, copy: bool = True,
+            no_tail_rule: bool = False) -> KminmersBatch:
         b = _as_u8(bases)
         so = np.ascontiguousarray(seq_off, dtype=np.uint64)
         if so.ndim != 1 or so.shape[0] < 1:
@@ -267,10 +268,13 @@ class Context:
         n = so.shape[0] - 1
         if int(so[-1]) > b.shape[0]:
             raise ValueError("seq_off[-1] exceeds len(bases)")
-        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 1 if want_minimizers else 0))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (1 if want_minimizers else 0) | (2 if no_tail_rule else 0)))
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
-        self._check(self.lib.c.s2k_run(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(p), C.byref(r)))
+        try:
+            self._check(self.lib.c.s2k_run(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(p), C.byref(r)))
+        finally:
+            self.lib.c.s2k_ctx_set_flags(self.h, 0)
         f = (lambda a: a.copy()) if copy else (lambda a: a)
         mins = f(_view(r.minimizers, r.n_minimizers, MINIMIZER_DTYPE)) if want_minimizers else None
         return KminmersBatch(n, f(_view(r.hash, r.n_items, np.uint64)), f(_view(r.start, r.n_items, np.uint32)),
@@ -280,12 +284,17 @@ class Context:
 
     # -- device buffers in, device results out ------------------------------------------------------------
     def run_device(self, d_bases_ptr: int, d_seq_off_ptr: int, n_seqs: int, n_bases: int, l: int, k: int,
-                   density: float, mode: HashMode, variant: HashVariant = HashVariant.NT1_32, stream: int = 0) -> _Result:
+                   density: float, mode: HashMode, variant: HashVariant = HashVariant.NT1_32, stream: int = 0,
+                   no_tail_rule: bool = False) -> _Result:
         """Raw device-pointer form (pointers as ints).  Returns the ctypes result struct (device pointers)."""
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
-        self._check(self.lib.c.s2k_run_device(self.h, C.c_void_p(d_bases_ptr), C.c_void_p(d_seq_off_ptr), int(n_seqs),
-                                              int(n_bases), C.byref(p), C.c_void_p(stream), C.byref(r)))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 2 if no_tail_rule else 0))
+        try:
+            self._check(self.lib.c.s2k_run_device(self.h, C.c_void_p(d_bases_ptr), C.c_void_p(d_seq_off_ptr), int(n_seqs),
+                                                  int(n_bases), C.byref(p), C.c_void_p(stream), C.byref(r)))
+        finally:
+            self.lib.c.s2k_ctx_set_flags(self.h, 0)
         return r
 
     def synth_device(self, seed: int, first: int, count: int, d_out_ptr: int, stream: int = 0):

@@ -186,7 +186,7 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     P.l = p->l; P.k = p->k;
     P.d = (p->mode == S2K_MODE_HPC) ? 1u : 0u;       // Hpc: the l-mer is emitted when the NEXT kept base shows up
     P.need = P.l - 1 + P.d;
-    P.quirk = P.simd && !P.w31;
+    P.quirk = P.simd && !P.w31 && !(ctx && (ctx->flags & S2K_NO_TAIL_RULE));
 #if S2K_WARP
     // warp-tile kernel: per-warp halo of 64 raw bases when that almost surely holds l-1(+1) kept bases, else 256
     P.halo = (P.hpc ? P.need <= 31 : P.need <= 64) ? 64u : 256u;

@@ -167,3 +167,26 @@ def test_pipelined_host_path(S, O, gpu_ctx, batches):
             assert_batch_matches_oracle(O, got, bases, so, 31, 3, 0.03, mode)
     finally:
         gpu_ctx.set_slab_bytes(0)
+
+
+def test_one_sequence_split_across_ranks(S, O, gpu_ctx):
+    """SURVEY 8(e), config 4 shape: a 30-Mbp sequence processed as 4 base ranges (overlap-and-trim by ownership) gives
+    exactly the k-min-mers of the whole sequence, for the 31-bit hash, the scalar HPC profile and ntHash1 HpcSimd
+    (whose AVX-512 tail rule needs the HPC length of the whole sequence)."""
+    import importlib
+    sharding = importlib.import_module("rust-seq2kminmers_b200.sharding")
+    n = 30_000_000
+    seq = O.synth(0x5EED0004, 0, n)
+    so = np.array([0, n], dtype=np.uint64)
+    l, k, d = 31, 5, 0.01
+    for mode, var in [(3, 1), (1, 0), (3, 0)]:
+        whole = gpu_ctx.run(seq, so, l, k, d, S.HashMode(mode), S.HashVariant(var))
+        ranges = sharding.sequence_ranges(n, 4, sharding.default_overlap_right(l, k, d))
+        kept = [sharding.kept_in_range(seq[lo:hi], lo, b0, b1, True) for (b0, b1, lo, hi) in ranges]
+        parts = [sharding.run_sequence_part(gpu_ctx, seq[lo:hi], lo, b0, b1, n, l, k, d, S.HashMode(mode), S.HashVariant(var),
+                                            kept_total=sum(kept)) for (b0, b1, lo, hi) in ranges]
+        assert sum(len(p["hash"]) for p in parts) == whole.n_items
+        assert np.array_equal(np.concatenate([p["hash"] for p in parts]), whole.hash)
+        assert np.array_equal(np.concatenate([p["start"] for p in parts]), whole.start.astype(np.uint64))
+        assert np.array_equal(np.concatenate([p["end"] for p in parts]), whole.end.astype(np.uint64))
+        assert np.array_equal(np.concatenate([p["rev"] for p in parts]), whole.rev)

@@ -68,3 +68,39 @@ def test_two_ranks_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_one_sequence_split_across_ranks_emulated():
+    """one long sequence cut into base ranges; overlap-and-trim by ownership == the whole sequence."""
+    import importlib
+    sys.path.insert(0, str(ROOT))
+    S = importlib.import_module("rust-seq2kminmers_b200")
+    sharding = importlib.import_module("rust-seq2kminmers_b200.sharding")
+    from oracle import oracle as O
+    subprocess.run([str(ROOT / "tests" / "emu" / "build_emu.sh")], check=True)
+    ctx = S.Context(0, S.Library(ROOT / "tests" / "emu" / "libs2k_emu.so"))
+    rng = np.random.default_rng(11)
+    base = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 90000)]
+    base[30000:30200] = ord("A")                      # a homopolymer across a cut
+    l, k, d = 31, 5, 0.02
+    for mode, var in [(1, 0), (3, 0), (2, 0), (0, 0), (3, 1)]:
+        seqs = [base]
+        if (mode, var) == (3, 0):                      # make the AVX-512 tail rule fire: trim until S % 16 == 0
+            for cut in range(0, 64):
+                s = base[:len(base) - cut]
+                if (len(O.encode_rle_simd(s)[0]) - l + 1) % 16 == 0:
+                    seqs.append(s)
+                    break
+        for seq in seqs:
+            want = O.kminmers(seq, l, k, d, mode, var)
+            for world in (2, 3):
+                ranges = sharding.sequence_ranges(len(seq), world, sharding.default_overlap_right(l, k, d))
+                kept = [sharding.kept_in_range(seq[lo:hi], lo, b0, b1, mode in (1, 3)) for (b0, b1, lo, hi) in ranges]
+                parts = []
+                for r, (b0, b1, lo, hi) in enumerate(ranges):
+                    parts.append(sharding.run_sequence_part(ctx, seq[lo:hi], lo, b0, b1, len(seq), l, k, d, S.HashMode(mode),
+                                                            S.HashVariant(var), kept_total=sum(kept)))
+                for key in ("hash", "start", "end", "rev"):
+                    cat = np.concatenate([p[key] for p in parts])
+                    assert np.array_equal(cat, want[key].astype(cat.dtype)), (mode, var, world, key, len(seq))
+    ctx.close()
