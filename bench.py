@@ -269,14 +269,16 @@ def main():
     if not args.no_e2e:
         hb = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
         hb.copy_(d_bases[:n_bases])
-        hso = (torch.arange(n_reads + 1, dtype=torch.int64) * L).pin_memory()
+        hso = d_so.cpu().pin_memory()
         hb_np, hso_np = hb.numpy(), hso.numpy().view(np.uint64)
         e_steps = args.steps
-        out = ctx.run(hb_np, hso_np, L_PARAM, K_PARAM, DENSITY, S.HashMode(mode), S.HashVariant(variant), copy=False)  # warm-up
+        out = ctx.run(hb_np, hso_np, L_PARAM, K_PARAM, DENSITY, S.HashMode(mode), S.HashVariant(variant), copy=False,
+                      no_tail_rule=split_one)  # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            out = ctx.run(hb_np, hso_np, L_PARAM, K_PARAM, DENSITY, S.HashMode(mode), S.HashVariant(variant), copy=False)
+            out = ctx.run(hb_np, hso_np, L_PARAM, K_PARAM, DENSITY, S.HashMode(mode), S.HashVariant(variant), copy=False,
+                          no_tail_rule=split_one)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
