@@ -107,6 +107,8 @@ typedef struct s2k_ctx s2k_ctx;
 
 /* Flags for s2k_ctx_set_flags. */
 #define S2K_WANT_MINIMIZERS 1u  /* s2k_run (host) also copies the minimizer stream back */
+#define S2K_GENERAL_KERNEL  4u  /* always use the general minimizer kernel (k_minimizers), never the raw-space fast path
+                                   (k_minimizers_fast); results are identical either way -- for tests and A/B timing */
 #define S2K_NO_TAIL_RULE    2u  /* do not apply the `(len-l+1) % 16 == 0` tail rule of src/nthash_avx512_32.rs:134-138:
                                    for callers that process one sequence in pieces (sharding.py) and apply the rule
                                    themselves from the length of the whole sequence */
@@ -169,6 +171,9 @@ const char *s2k_strerror(int status);
 int s2k_abi_version(void);
 /* Kernels launched by the context since creation (for benchmark bookkeeping). */
 uint64_t s2k_launch_count(const s2k_ctx *ctx);
+/* Which minimizer kernel the last run used: 0 = general (k_minimizers), 1 = raw-space fast path (k_minimizers_fast),
+ * 2 = the fast path declined (non-ACGT bases, long homopolymers, very dense selection) and the general kernel reran. */
+int s2k_last_kernel_kind(const s2k_ctx *ctx);
 /* Name and average duration (ms) of the context's dominant kernel over the last s2k_run_device call,
  * measured with CUDA events on the launching stream when timing is enabled. */
 int s2k_ctx_set_timing(s2k_ctx *ctx, int enabled);

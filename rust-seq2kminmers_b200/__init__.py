@@ -81,7 +81,7 @@ ABI_SYMBOLS = (
     "s2k_ctx_create", "s2k_ctx_destroy", "s2k_ctx_set_flags", "s2k_run", "s2k_run_device", "s2k_encode_rle",
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
-    "s2k_ctx_set_slab_bytes",
+    "s2k_ctx_set_slab_bytes", "s2k_last_kernel_kind",
 )
 
 
@@ -126,6 +126,8 @@ class Library:
         L.s2k_ctx_set_timing.argtypes = [vp, C.c_int]
         L.s2k_ctx_set_slab_bytes.restype = C.c_int
         L.s2k_ctx_set_slab_bytes.argtypes = [vp, C.c_uint64]
+        L.s2k_last_kernel_kind.restype = C.c_int
+        L.s2k_last_kernel_kind.argtypes = [vp]
         L.s2k_synth_device.restype = C.c_int
         L.s2k_synth_device.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
         L.s2k_last_kernel_ms.restype = C.c_int
@@ -260,7 +262,7 @@ class Context:
     # -- host buffers in, host (pinned) results out ------------------------------------------------------
     def run(self, bases, seq_off, l: int, k: int, density: float, mode: HashMode,
             variant: HashVariant = HashVariant.NT1_32, want_minimizers: bool = False, copy: bool = True,
-            no_tail_rule: bool = False) -> KminmersBatch:
+            no_tail_rule: bool = False, general_kernel: bool = False) -> KminmersBatch:
         b = _as_u8(bases)
         so = np.ascontiguousarray(seq_off, dtype=np.uint64)
         if so.ndim != 1 or so.shape[0] < 1:
@@ -268,7 +270,8 @@ class Context:
         n = so.shape[0] - 1
         if int(so[-1]) > b.shape[0]:
             raise ValueError("seq_off[-1] exceeds len(bases)")
-        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (1 if want_minimizers else 0) | (2 if no_tail_rule else 0)))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (1 if want_minimizers else 0) | (2 if no_tail_rule else 0) |
+                                                 (4 if general_kernel else 0)))
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
         try:
@@ -285,11 +288,11 @@ class Context:
     # -- device buffers in, device results out ------------------------------------------------------------
     def run_device(self, d_bases_ptr: int, d_seq_off_ptr: int, n_seqs: int, n_bases: int, l: int, k: int,
                    density: float, mode: HashMode, variant: HashVariant = HashVariant.NT1_32, stream: int = 0,
-                   no_tail_rule: bool = False) -> _Result:
+                   no_tail_rule: bool = False, general_kernel: bool = False) -> _Result:
         """Raw device-pointer form (pointers as ints).  Returns the ctypes result struct (device pointers)."""
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
-        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 2 if no_tail_rule else 0))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (2 if no_tail_rule else 0) | (4 if general_kernel else 0)))
         try:
             self._check(self.lib.c.s2k_run_device(self.h, C.c_void_p(d_bases_ptr), C.c_void_p(d_seq_off_ptr), int(n_seqs),
                                                   int(n_bases), C.byref(p), C.c_void_p(stream), C.byref(r)))
@@ -322,6 +325,11 @@ class Context:
         a, b, n = C.c_double(), C.c_double(), C.c_uint32()
         self._check(self.lib.c.s2k_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    @property
+    def last_kernel_kind(self) -> int:
+        """0 general kernel, 1 raw-space fast kernel, 2 fast kernel declined and the general one reran."""
+        return int(self.lib.c.s2k_last_kernel_kind(self.h))
 
     @property
     def launch_count(self) -> int:

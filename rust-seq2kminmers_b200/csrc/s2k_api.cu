@@ -95,6 +95,7 @@ struct s2k_ctx {
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
     bool attr_set = false;
+    int kernel_kind = 0;            // last run: 0 general kernel, 1 fast kernel, 2 fast kernel declined -> general
     // pipelined host path (s2k_run on large batches)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_out = nullptr, ev_done = nullptr;
@@ -164,6 +165,8 @@ struct Plan {
     bool hpc, simd, w31, quirk;
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
+    bool fast_ok;    // k_minimizers_fast covers this plan (HPC mode, 20 <= l <= 31, moderate density)
+    uint32_t fh0, rh0, hcap;
     uint8_t lut[256];   // raw byte -> code of its base class
     uint2 xy[XYN];
 };
@@ -218,6 +221,15 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         P.lut['A'] = code_of[0]; P.lut['C'] = code_of[1]; P.lut['G'] = code_of[2]; P.lut['T'] = code_of[3];
         P.lut['N'] = code_of[4];
     }
+    {   // raw-space fast kernel: initial state = l bases 'A' (FIFO of zeros), hit list sized from the selection rate
+        P.fh0 = P.rh0 = 0;
+        for (uint32_t i = 0; i < P.l; ++i) { P.fh0 ^= rolw(h[0], i, w); P.rh0 ^= rolw(rc[0], i, w); }
+        const double frac = P.none ? 0.0 : std::min(1.0, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+        const double mean = 256.0 * std::min(1.0, 2.0 * frac);
+        const double want = 4.0 * mean + 16.0;
+        P.hcap = (uint32_t)std::min(128.0, std::max(16.0, want));
+        P.fast_ok = P.hpc && P.l >= 20 && P.l <= 31 && want <= 128.0 && !(ctx && (ctx->flags & S2K_GENERAL_KERNEL));
+    }
     std::memset(P.xy, 0, sizeof(P.xy));
     for (int o = 0; o < 6; ++o)
         for (int i = 0; i < 6; ++i) {
@@ -239,6 +251,9 @@ int set_attrs(s2k_ctx *ctx)
     CU(cudaFuncSetAttribute(k_minimizers<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_minimizers<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_minimizers<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(k_minimizers_fast<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
+    CU(cudaFuncSetAttribute(k_minimizers_fast<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
+    CU(cudaFuncSetAttribute(k_minimizers_fast<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
     CU(cudaFuncSetAttribute(k_minimizers_w<false, false, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<68>)));
     CU(cudaFuncSetAttribute(k_minimizers_w<false, true, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<68>)));
     CU(cudaFuncSetAttribute(k_minimizers_w<true, false, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<52>)));
@@ -293,19 +308,6 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         return S2K_OK;
     }
 
-    const uint64_t n_tiles64 = (n_bases + P.tile - 1) / P.tile;
-    if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
-    const uint32_t n_tiles = (uint32_t)n_tiles64;
-#if S2K_WARP
-    const int max_grid = ctx->sm_count * 3;
-    const size_t hscr_words = (size_t)max_grid * 8 * HSW;
-#else
-    const int max_grid = ctx->sm_count * S2K_MINB;
-    const size_t hscr_words = (size_t)max_grid * WIN;
-#endif
-    if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_status, ((n_seqs + RT * RPT - 1) / (RT * RPT)) * 8 + 8, false))) return rc;
 
     // capacity of the minimizer stream: expected 2*density*(kept bases), with head room; grown and rerun on overflow
@@ -317,50 +319,83 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         cap = std::min<uint64_t>(n_bases, (uint64_t)((double)n_bases * rate) + 65536);
     }
 
-    K1Args A;
-    A.bases = d_bases; A.seq_off = d_seq_off;
-    A.tile_lb = ptr<uint32_t>(ctx->d_tile_lb);
-    A.ticket = reinterpret_cast<uint32_t *>(small + 4);
-    A.cursor = reinterpret_cast<unsigned long long *>(small + 0);
-    A.tile_info = ptr<uint4>(ctx->d_tile_info);
-    A.min_off = ptr<uint64_t>(ctx->d_min_off);
-    A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
-    A.hscr = ptr<uint32_t>(ctx->d_hscr);
-    A.err = reinterpret_cast<uint32_t *>(small + 5);
-    A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
-    A.tile = P.tile; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
-    std::memcpy(A.cls_lut, P.lut, 256);
-    std::memcpy(A.xy, P.xy, sizeof(P.xy));
-    S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, n_bases, P.tile, n_tiles,
-               ptr<uint32_t>(ctx->d_tile_lb));
-    ctx->launches += 1;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // Two minimizer kernels with identical outputs: k_minimizers_fast (raw-space rolling, register FIFO) for the plans
+    // it covers, k_minimizers for everything else and whenever the fast one declines (ERR_FAST).
+    bool use_fast = P.fast_ok;
+    uint32_t n_tiles = 0, tile_eff = 0;
+    ctx->kernel_kind = 0;
+    for (int attempt = 0;; ++attempt) {
+        if (attempt == 4) return fail(ctx, S2K_ERR_INTERNAL, "minimizer kernel did not converge");
+        tile_eff = use_fast ? (uint32_t)FTILE : P.tile;
+        const uint64_t n_tiles64 = (n_bases + tile_eff - 1) / tile_eff;
+        if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
+        n_tiles = (uint32_t)n_tiles64;
+        int max_grid;
+        size_t hscr_words, smem;
+        void (*kfn)(const K1Args);
+        if (use_fast) {
+            max_grid = ctx->sm_count * 4;
+            hscr_words = (size_t)max_grid * NT * 2 * P.hcap;
+            smem = sizeof(SmemF);
+            kfn = P.w31 ? k_minimizers_fast<true, 0> : (P.d ? k_minimizers_fast<false, 1> : k_minimizers_fast<false, 0>);
+        } else {
+#if S2K_WARP
+            max_grid = ctx->sm_count * 3;
+            hscr_words = (size_t)max_grid * 8 * HSW;
+            smem = P.hpc ? sizeof(SmemW<52>) : sizeof(SmemW<68>);
+            kfn = P.hpc ? (P.w31 ? k_minimizers_w<true, true, 52> : k_minimizers_w<true, false, 52>)
+                        : (P.w31 ? k_minimizers_w<false, true, 68> : k_minimizers_w<false, false, 68>);
+#else
+            max_grid = ctx->sm_count * S2K_MINB;
+            hscr_words = (size_t)max_grid * WIN;
+            smem = sizeof(Smem);
+            kfn = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
+                        : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
+#endif
+        }
+        if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_tmp, cap * sizeof(uint4), false))) return rc;
+
+        K1Args A;
+        A.bases = d_bases; A.seq_off = d_seq_off;
+        A.tile_lb = ptr<uint32_t>(ctx->d_tile_lb);
+        A.ticket = reinterpret_cast<uint32_t *>(small + 4);
+        A.cursor = reinterpret_cast<unsigned long long *>(small + 0);
+        A.tile_info = ptr<uint4>(ctx->d_tile_info);
         A.min_out = ptr<uint4>(ctx->d_tmp); A.min_cap = cap;
+        A.min_off = ptr<uint64_t>(ctx->d_min_off);
+        A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+        A.hscr = ptr<uint32_t>(ctx->d_hscr);
+        A.err = reinterpret_cast<uint32_t *>(small + 5);
+        A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
+        A.tile = tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
+        A.fast_fh0 = P.fh0; A.fast_rh0 = P.rh0; A.fast_hcap = P.hcap;
+        std::memcpy(A.cls_lut, P.lut, 256);
+        std::memcpy(A.xy, P.xy, sizeof(P.xy));
         CU(cudaMemsetAsync(small, 0, 64, st));
+        S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, n_bases, tile_eff, n_tiles,
+                   ptr<uint32_t>(ctx->d_tile_lb));
         const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
         Timing &T = ctx->tm;
         const bool rec = T.enabled && T.n < 64;
         if (rec) cudaEventRecord(T.ev[T.n][0], st);
-#if S2K_WARP
-        const size_t smem = P.hpc ? sizeof(SmemW<52>) : sizeof(SmemW<68>);
-        void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers_w<true, true, 52> : k_minimizers_w<true, false, 52>)
-                                          : (P.w31 ? k_minimizers_w<false, true, 68> : k_minimizers_w<false, false, 68>);
-#else
-        const size_t smem = sizeof(Smem);
-        void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
-                                          : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
-#endif
         S2K_LAUNCH(kfn, grid, NT, smem, st, true, A);
         if (rec) { cudaEventRecord(T.ev[T.n][1], st); ++T.n; }
         CU(cudaGetLastError());
-        ctx->launches += 1;
+        ctx->launches += 2;
         CU(cudaMemcpyAsync(hsmall, small, 8, cudaMemcpyDeviceToHost, st));          // record cursor == total minimizers
         CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (use_fast && ((uint32_t)hsmall[2] & ERR_FAST)) {   // outside the fast kernel's model: redo with the general one
+            use_fast = false;
+            ctx->kernel_kind = 2;
+            continue;
+        }
+        if (use_fast) ctx->kernel_kind = 1;
         n_min = hsmall[0];
         if (n_min <= cap) break;
-        if (attempt == 1) return fail(ctx, S2K_ERR_INTERNAL, "minimizer capacity overflow after regrow");
         cap = n_min;                                   // exact size known now: rerun once
     }
     if ((rc = ensure(ctx, ctx->d_mins, std::max<uint64_t>(n_min, 1) * sizeof(uint4), false))) return rc;
@@ -378,7 +413,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         F.tile_info = ptr<uint4>(ctx->d_tile_info); F.tile_loc = tile_loc; F.chunk_base = chunk_base;
         F.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
         F.min_off = ptr<uint64_t>(ctx->d_min_off); F.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
-        F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = cap; F.n_tiles = n_tiles; F.tile = P.tile;
+        F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = cap; F.n_tiles = n_tiles; F.tile = tile_eff;
         const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 8);
         S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
         CU(cudaGetLastError());
@@ -561,6 +596,7 @@ int s2k_last_kernel_ms(const s2k_ctx *ctx, double *minimizer_ms, double *window_
 }
 
 uint64_t s2k_launch_count(const s2k_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int s2k_last_kernel_kind(const s2k_ctx *ctx) { return ctx ? ctx->kernel_kind : -1; }
 
 int s2k_host_alloc(size_t bytes, void **out)
 {
