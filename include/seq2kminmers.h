@@ -107,8 +107,8 @@ typedef struct s2k_ctx s2k_ctx;
 
 /* Flags for s2k_ctx_set_flags. */
 #define S2K_WANT_MINIMIZERS 1u  /* s2k_run (host) also copies the minimizer stream back */
-#define S2K_GENERAL_KERNEL  4u  /* always use the general minimizer kernel (k_minimizers), never the raw-space fast path
-                                   (k_minimizers_fast); results are identical either way -- for tests and A/B timing */
+#define S2K_GENERAL_KERNEL  4u  /* only meaningful in builds with -DS2K_FAST=1 (an experiment, off by default): use the
+                                   general minimizer kernel even where the raw-space variant applies; results identical */
 #define S2K_NO_TAIL_RULE    2u  /* do not apply the `(len-l+1) % 16 == 0` tail rule of src/nthash_avx512_32.rs:134-138:
                                    for callers that process one sequence in pieces (sharding.py) and apply the rule
                                    themselves from the length of the whole sequence */
@@ -171,8 +171,8 @@ const char *s2k_strerror(int status);
 int s2k_abi_version(void);
 /* Kernels launched by the context since creation (for benchmark bookkeeping). */
 uint64_t s2k_launch_count(const s2k_ctx *ctx);
-/* Which minimizer kernel the last run used: 0 = general (k_minimizers), 1 = raw-space fast path (k_minimizers_fast),
- * 2 = the fast path declined (non-ACGT bases, long homopolymers, very dense selection) and the general kernel reran. */
+/* Which minimizer kernel the last run used: 0 = k_minimizers (always, in default builds); in -DS2K_FAST=1 builds
+ * 1 = k_minimizers_fast, 2 = it declined (non-ACGT bases, long homopolymers, dense selection) and k_minimizers reran. */
 int s2k_last_kernel_kind(const s2k_ctx *ctx);
 /* Name and average duration (ms) of the context's dominant kernel over the last s2k_run_device call,
  * measured with CUDA events on the launching stream when timing is enabled. */

@@ -15,8 +15,12 @@
 
 using namespace s2k;
 
+// Build-time experiments, both bit-exact and both measured SLOWER than k_minimizers on B200:
 #ifndef S2K_WARP
-#define S2K_WARP 0                  // 1: k_minimizers_w (warp-independent sub-tiles), 0: k_minimizers
+#define S2K_WARP 0                  // 1: k_minimizers_w (warp-independent sub-tiles) replaces k_minimizers
+#endif
+#ifndef S2K_FAST
+#define S2K_FAST 0                  // 1: try k_minimizers_fast (raw-space rolling, register FIFO) first, fall back when it declines
 #endif
 
 // Kernel launch.  `conc` only matters to the test-tier host emulation (tests/emu): kernels with static shared
@@ -228,7 +232,7 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         const double mean = 256.0 * std::min(1.0, 2.0 * frac);
         const double want = 4.0 * mean + 16.0;
         P.hcap = (uint32_t)std::min(128.0, std::max(16.0, want));
-        P.fast_ok = P.hpc && P.l >= 20 && P.l <= 31 && want <= 128.0 && !(ctx && (ctx->flags & S2K_GENERAL_KERNEL));
+        P.fast_ok = S2K_FAST && P.hpc && P.l >= 20 && P.l <= 31 && want <= 128.0 && !(ctx && (ctx->flags & S2K_GENERAL_KERNEL));
     }
     std::memset(P.xy, 0, sizeof(P.xy));
     for (int o = 0; o < 6; ++o)
