@@ -59,6 +59,7 @@ typedef enum s2k_hash_variant {
 #define S2K_ERR_BAD_OFFSETS  -5   /* seq_off[0] != 0, decreasing offsets, or a sequence of >= 2^32 bases */
 #define S2K_ERR_INTERNAL     -6   /* device-side consistency check failed */
 #define S2K_ERR_NULL         -7
+#define S2K_ERR_IO           -8
 
 /* Arguments of KminmersIterator::new after `seq` (src/lib.rs:89). */
 typedef struct s2k_params {
@@ -130,6 +131,14 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
 /* Large host batches are streamed through the device in slabs cut at sequence boundaries (H2D, kernels and D2H
  * overlap on three streams).  bytes = target slab size (0 = default 256 MiB); batches up to 1.5 slabs go in one piece. */
 int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes);
+
+/* Host ingest + run: the loop of the reference's driver, `parallel_fastx(&filename, nb_threads, task)` with
+ * `task = |seq, id| KminmersIterator::new(seq, l, k, density, mode)` (src/main.rs:65-79; rust-parallelfastx is an
+ * external crate).  `path` is a plain-text FASTA (multi-line allowed) or 4-line FASTQ file; it is mapped and parsed on
+ * nb_threads host threads straight into pinned memory (line ends stripped, records in file order), then goes through
+ * s2k_run.  s2k_last_fastx returns the parsed batch (pointers owned by the context, valid until the next fastx call). */
+int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_params *params, s2k_result *out);
+int s2k_last_fastx(const s2k_ctx *ctx, uint64_t *n_seqs, uint64_t *n_bases, const uint8_t **bases, const uint64_t **seq_off);
 
 /* Same, DEVICE buffers already resident in HBM (bases 16-byte aligned); results stay on the device.
  * `stream` is a cudaStream_t (NULL = the context's own stream).  Returns after the launch sequence has been

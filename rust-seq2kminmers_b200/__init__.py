@@ -81,7 +81,7 @@ ABI_SYMBOLS = (
     "s2k_ctx_create", "s2k_ctx_destroy", "s2k_ctx_set_flags", "s2k_run", "s2k_run_device", "s2k_encode_rle",
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
-    "s2k_ctx_set_slab_bytes", "s2k_last_kernel_kind",
+    "s2k_ctx_set_slab_bytes", "s2k_last_kernel_kind", "s2k_run_fastx", "s2k_last_fastx",
 )
 
 
@@ -126,6 +126,10 @@ class Library:
         L.s2k_ctx_set_timing.argtypes = [vp, C.c_int]
         L.s2k_ctx_set_slab_bytes.restype = C.c_int
         L.s2k_ctx_set_slab_bytes.argtypes = [vp, C.c_uint64]
+        L.s2k_run_fastx.restype = C.c_int
+        L.s2k_run_fastx.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(_Params), C.POINTER(_Result)]
+        L.s2k_last_fastx.restype = C.c_int
+        L.s2k_last_fastx.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
         L.s2k_last_kernel_kind.restype = C.c_int
         L.s2k_last_kernel_kind.argtypes = [vp]
         L.s2k_synth_device.restype = C.c_int
@@ -299,6 +303,24 @@ class Context:
         finally:
             self.lib.c.s2k_ctx_set_flags(self.h, 0)
         return r
+
+    def run_fastx(self, path, nb_threads: int, l: int, k: int, density: float, mode: HashMode,
+                  variant: HashVariant = HashVariant.NT1_32, copy: bool = True):
+        """parallel_fastx(path, nb_threads, |seq, id| KminmersIterator::new(seq, l, k, density, mode)) of src/main.rs:65-79.
+        Returns (KminmersBatch, bases u8[], seq_off u64[]) -- the parsed records in file order and their k-min-mers."""
+        p = _Params(int(l), int(k), float(density), int(mode), int(variant))
+        r = _Result()
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 0))
+        self._check(self.lib.c.s2k_run_fastx(self.h, str(path).encode(), int(nb_threads), C.byref(p), C.byref(r)))
+        ns, nb, pb, po = C.c_uint64(), C.c_uint64(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.c.s2k_last_fastx(self.h, C.byref(ns), C.byref(nb), C.byref(pb), C.byref(po)))
+        f = (lambda a: a.copy()) if copy else (lambda a: a)
+        n = int(ns.value)
+        batch = KminmersBatch(n, f(_view(r.hash, r.n_items, np.uint64)), f(_view(r.start, r.n_items, np.uint32)),
+                              f(_view(r.end, r.n_items, np.uint32)), f(_view(r.rev, r.n_items, np.uint8)),
+                              f(_view(r.km_off, n + 1, np.uint64)), f(_view(r.min_off, n + 1, np.uint64)),
+                              f(_view(r.min_cnt, n, np.uint32)), int(r.n_minimizers), None)
+        return batch, f(_view(pb.value, int(nb.value), np.uint8)), f(_view(po.value, n + 1, np.uint64))
 
     def synth_device(self, seed: int, first: int, count: int, d_out_ptr: int, stream: int = 0):
         """Fill device memory with the synthetic base stream of SURVEY.md 8(d)."""

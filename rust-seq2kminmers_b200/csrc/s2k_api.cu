@@ -106,6 +106,8 @@ struct s2k_ctx {
     bool pipe_ready = false;
     uint64_t slab_bytes = 0;        // 0 = default
     Buf d_in[2], d_in_off[2], h_off_stage[2];
+    Buf h_fx_bases, h_fx_off;       // s2k_run_fastx: parsed file in pinned memory
+    uint64_t fx_n_seqs = 0, fx_n_bases = 0;
 };
 
 namespace {
@@ -115,6 +117,7 @@ int fail(s2k_ctx *c, int code, const std::string &msg)
     if (c) c->err = msg;
     return code;
 }
+#define CU_PLACEHOLDER
 #define CU(call)                                                                                     \
     do {                                                                                             \
         cudaError_t e__ = (call);                                                                    \
@@ -164,6 +167,10 @@ void release(Buf &b)
     if (b.p) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
     b.p = nullptr; b.cap = 0;
 }
+
+} // namespace
+#include "s2k_fastx.inc"
+namespace {
 
 struct Plan {
     bool hpc, simd, w31, quirk;
@@ -517,6 +524,7 @@ const char *s2k_strerror(int status)
     case S2K_ERR_BAD_OFFSETS: return "invalid sequence offsets";
     case S2K_ERR_INTERNAL: return "internal device-side check failed";
     case S2K_ERR_NULL: return "null pointer";
+    case S2K_ERR_IO: return "input file error";
     default: return "unknown status";
     }
 }
@@ -561,7 +569,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
                   &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in_off[0], &ctx->d_in_off[1],
-                  &ctx->h_off_stage[0], &ctx->h_off_stage[1]};
+                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_fx_bases, &ctx->h_fx_off};
     for (Buf *b : all) release(*b);
     if (ctx->tm.created) {
         for (auto &e : ctx->tm.ev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
@@ -843,6 +851,69 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
     out->min_off = ptr<uint64_t>(ctx->h_min_off);
     out->min_cnt = ptr<uint32_t>(ctx->h_min_cnt);
     out->minimizers = want_min ? reinterpret_cast<const s2k_minimizer *>(ctx->h_mins.p) : nullptr;
+    return S2K_OK;
+}
+
+int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_params *params, s2k_result *out)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (!path || !out) return fail(ctx, S2K_ERR_NULL, "null argument");
+    if (nb_threads < 1) nb_threads = 1;
+    FxFile f;
+    f.fd = open(path, O_RDONLY);
+    if (f.fd < 0) return fail(ctx, S2K_ERR_IO, std::string("cannot open ") + path);
+    struct stat st;
+    if (fstat(f.fd, &st) != 0) return fail(ctx, S2K_ERR_IO, std::string("cannot stat ") + path);
+    f.n = (size_t)st.st_size;
+    if (f.n) {
+        void *m = mmap(nullptr, f.n, PROT_READ, MAP_PRIVATE, f.fd, 0);
+        if (m == MAP_FAILED) { f.n = 0; return fail(ctx, S2K_ERR_IO, std::string("cannot map ") + path); }
+        f.p = (const char *)m;
+    }
+    size_t first = 0;
+    while (first < f.n && (f.p[first] == '\n' || f.p[first] == '\r' || f.p[first] == ' ')) ++first;
+    if (first < f.n && f.p[first] != '>' && f.p[first] != '@')
+        return fail(ctx, S2K_ERR_IO, "not a FASTA/FASTQ file (first record must start with '>' or '@')");
+    const bool fastq = first < f.n && f.p[first] == '@';
+    const int T = (int)std::min<size_t>((size_t)nb_threads, std::max<size_t>(1, f.n >> 16));
+    std::vector<std::vector<FxRec>> recs((size_t)T);
+    std::vector<uint64_t> nb((size_t)T, 0);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t]() { fx_scan(f.p, f.n, f.n * (size_t)t / T, f.n * (size_t)(t + 1) / T, fastq, recs[t], nb[t]); });
+        for (auto &x : th) x.join();
+    }
+    uint64_t n_seqs = 0, n_bases = 0;
+    std::vector<uint64_t> seq_base((size_t)T), byte_base((size_t)T);
+    for (int t = 0; t < T; ++t) { seq_base[t] = n_seqs; byte_base[t] = n_bases; n_seqs += recs[t].size(); n_bases += nb[t]; }
+    int rc;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = ensure(ctx, ctx->h_fx_bases, n_bases + 64, true))) return rc;
+    if ((rc = ensure(ctx, ctx->h_fx_off, (n_seqs + 1) * 8, true))) return rc;
+    uint8_t *hb = ptr<uint8_t>(ctx->h_fx_bases);
+    uint64_t *ho = ptr<uint64_t>(ctx->h_fx_off);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+                uint64_t o = byte_base[t], i = seq_base[t];
+                for (const FxRec &r : recs[t]) { ho[i++] = o; fx_copy(f.p, r, hb + o, fastq); o += r.n; }
+            });
+        for (auto &x : th) x.join();
+    }
+    ho[n_seqs] = n_bases;
+    ctx->fx_n_seqs = n_seqs; ctx->fx_n_bases = n_bases;
+    return s2k_run(ctx, hb, ho, n_seqs, params, out);
+}
+
+int s2k_last_fastx(const s2k_ctx *ctx, uint64_t *n_seqs, uint64_t *n_bases, const uint8_t **bases, const uint64_t **seq_off)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (n_seqs) *n_seqs = ctx->fx_n_seqs;
+    if (n_bases) *n_bases = ctx->fx_n_bases;
+    if (bases) *bases = reinterpret_cast<const uint8_t *>(ctx->h_fx_bases.p);
+    if (seq_off) *seq_off = reinterpret_cast<const uint64_t *>(ctx->h_fx_off.p);
     return S2K_OK;
 }
 

@@ -65,3 +65,30 @@ def cases(B, fixture_seq, scale=1):
             (31, 70, 0.05, HPC, 0)]
     out.append(("dense", b, so, par))
     return out
+
+
+def fuzz_cases(B, n_cases, max_len):
+    """Random (batch, parameters): every mode/variant, l across the allowed range, k, density over four decades,
+    batch shapes from many tiny reads to a few long ones, alphabets with and without non-ACGT bytes."""
+    rng = B.rng
+    out = []
+    for _ in range(n_cases):
+        mode = int(rng.integers(0, 4))
+        variant = int(rng.integers(0, 2)) if mode in (SIMD, HPCSIMD) else 0
+        l = int(rng.integers(1, 32)) if mode in (SIMD, HPCSIMD) else int(rng.choice([rng.integers(1, 32), rng.integers(32, 256)]))
+        k = int(rng.choice([1, 2, 3, 5, 8, 10, 33]))
+        d = float(10 ** rng.uniform(-3.3, 0.0))
+        shape = int(rng.integers(0, 4))
+        if shape == 0:
+            lens = list(rng.integers(0, 3 * l + 40, int(rng.integers(1, 400))))
+        elif shape == 1:
+            lens = [150] * int(rng.integers(1, 300))
+        elif shape == 2:
+            lens = list(rng.integers(1000, max_len, int(rng.integers(1, 5))))
+        else:
+            lens = list(rng.integers(0, 2000, int(rng.integers(1, 60)))) + [int(rng.integers(20000, max_len))]
+        alphabet = [b"ACGT", b"ACGT", b"ACGTN", b"ACGTacgtNnRY"][int(rng.integers(0, 4))]
+        runp = float(rng.choice([0.0, 0.0, 0.3, 0.8]))
+        bases, so = B.batch(lens, alphabet=alphabet, runp=runp)
+        out.append((bases, so, (l, k, d, mode, variant)))
+    return out

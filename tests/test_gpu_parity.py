@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_batch_matches_oracle
-from parity_cases import cases
+from parity_cases import cases, fuzz_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -190,3 +190,10 @@ def test_one_sequence_split_across_ranks(S, O, gpu_ctx):
         assert np.array_equal(np.concatenate([p["start"] for p in parts]), whole.start.astype(np.uint64))
         assert np.array_equal(np.concatenate([p["end"] for p in parts]), whole.end.astype(np.uint64))
         assert np.array_equal(np.concatenate([p["rev"] for p in parts]), whole.rev)
+
+
+def test_random_parameter_fuzz(S, O, gpu_ctx, batches):
+    """120 random (batch, mode, variant, l, k, density) draws, full tuples and minimizer streams against the oracle."""
+    for bases, so, (l, k, d, mode, var) in fuzz_cases(batches, 120, 120000):
+        got = gpu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)
+        assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
