@@ -14,7 +14,9 @@ pytestmark = pytest.mark.gpu
 
 def test_library_is_the_cuda_build(S, gpu_ctx):
     assert S.LIB_PATH.exists() and gpu_ctx.lib.path == S.LIB_PATH
-    assert gpu_ctx.launch_count == 0
+    n0 = gpu_ctx.launch_count
+    gpu_ctx.run(np.frombuffer(b"ACGT" * 50, dtype=np.uint8), np.array([0, 200], dtype=np.uint64), 5, 2, 0.5, S.HashMode.Hpc)
+    assert gpu_ctx.launch_count > n0 and gpu_ctx.last_kernel_kind == 0
 
 
 def test_parity_cases_full_tuples(S, O, gpu_ctx, batches, fixture_seq):
