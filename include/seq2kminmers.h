@@ -110,6 +110,7 @@ typedef struct s2k_ctx s2k_ctx;
 #define S2K_WANT_MINIMIZERS 1u  /* s2k_run (host) also copies the minimizer stream back */
 #define S2K_GENERAL_KERNEL  4u  /* only meaningful in builds with -DS2K_FAST=1 (an experiment, off by default): use the
                                    general minimizer kernel even where the raw-space variant applies; results identical */
+#define S2K_DEBUG_TINY_CAP  8u  /* tests only: start with room for 1000 minimizers so that the grow-and-rerun path runs */
 #define S2K_NO_TAIL_RULE    2u  /* do not apply the `(len-l+1) % 16 == 0` tail rule of src/nthash_avx512_32.rs:134-138:
                                    for callers that process one sequence in pieces (sharding.py) and apply the rule
                                    themselves from the length of the whole sequence */

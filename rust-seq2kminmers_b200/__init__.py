@@ -266,7 +266,7 @@ class Context:
     # -- host buffers in, host (pinned) results out ------------------------------------------------------
     def run(self, bases, seq_off, l: int, k: int, density: float, mode: HashMode,
             variant: HashVariant = HashVariant.NT1_32, want_minimizers: bool = False, copy: bool = True,
-            no_tail_rule: bool = False, general_kernel: bool = False) -> KminmersBatch:
+            no_tail_rule: bool = False, general_kernel: bool = False, debug_tiny_cap: bool = False) -> KminmersBatch:
         b = _as_u8(bases)
         so = np.ascontiguousarray(seq_off, dtype=np.uint64)
         if so.ndim != 1 or so.shape[0] < 1:
@@ -275,7 +275,7 @@ class Context:
         if int(so[-1]) > b.shape[0]:
             raise ValueError("seq_off[-1] exceeds len(bases)")
         self._check(self.lib.c.s2k_ctx_set_flags(self.h, (1 if want_minimizers else 0) | (2 if no_tail_rule else 0) |
-                                                 (4 if general_kernel else 0)))
+                                                 (4 if general_kernel else 0) | (8 if debug_tiny_cap else 0)))
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
         try:

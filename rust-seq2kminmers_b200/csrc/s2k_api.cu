@@ -328,6 +328,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         double rate = std::min(1.0, 2.0 * frac) * 1.15 + 0.0005;
         rate = std::max(rate, ctx->rate_hint * 1.05);
         cap = std::min<uint64_t>(n_bases, (uint64_t)((double)n_bases * rate) + 65536);
+        if (ctx->flags & S2K_DEBUG_TINY_CAP) cap = std::min<uint64_t>(cap, 1000);
     }
 
     // Two minimizer kernels with identical outputs: k_minimizers_fast (raw-space rolling, register FIFO) for the plans

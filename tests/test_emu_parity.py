@@ -104,3 +104,12 @@ def test_experimental_kernels_stay_exact(S, O, batches, fixture_seq, tmp_path, d
             assert kinds == {0, 1, 2}      # general (non-HPC / short l), fast, fast declined -> general
     finally:
         ctx.close()
+
+
+def test_capacity_overflow_reruns_emulated(S, O, emu_ctx, batches):
+    """The minimizer buffer is sized from the expected selection rate; when a batch is denser the kernel reports the
+    exact count and the host reruns once with that size.  Forced here with a 1000-record start capacity."""
+    bases, so = batches.batch([40000, 150, 9000])
+    got = emu_ctx.run(bases, so, 15, 3, 0.3, S.HashMode.Hpc, want_minimizers=True, debug_tiny_cap=True)
+    assert got.n_minimizers > 1000
+    assert_batch_matches_oracle(O, got, bases, so, 15, 3, 0.3, 1)

@@ -199,3 +199,39 @@ def test_random_parameter_fuzz(S, O, gpu_ctx, batches):
     for bases, so, (l, k, d, mode, var) in fuzz_cases(batches, 120, 120000):
         got = gpu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)
         assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
+
+
+def test_capacity_overflow_reruns(S, O, gpu_ctx, batches):
+    bases, so = batches.batch([200000, 150, 9000, 150000])
+    for mode in (S.HashMode.Hpc, S.HashMode.Simd):
+        got = gpu_ctx.run(bases, so, 15, 3, 0.3, mode, want_minimizers=True, debug_tiny_cap=True)
+        assert got.n_minimizers > 1000
+        assert_batch_matches_oracle(O, got, bases, so, 15, 3, 0.3, int(mode))
+
+
+def test_contexts_on_concurrent_host_threads(S, O, batches):
+    """include/seq2kminmers.h: a context is single-threaded, distinct contexts may run concurrently from distinct host
+    threads (one stream each) -- the pattern of one context per worker thread in INTEGRATION.md."""
+    import threading
+    work = []
+    for i in range(4):
+        bases, so = batches.batch([150] * 2000 + [20000] * 20 + [int(x) for x in batches.rng.integers(0, 3000, 200)])
+        work.append((bases, so, [S.HashMode.HpcSimd, S.HashMode.Hpc, S.HashMode.Simd, S.HashMode.Regular][i]))
+    results, errors = [None] * 4, []
+
+    def worker(i):
+        try:
+            with S.Context(0) as ctx:
+                for _ in range(5):
+                    results[i] = ctx.run(work[i][0], work[i][1], 31, 5, 0.02, work[i][2], want_minimizers=True)
+        except Exception as e:          # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(4):
+        assert_batch_matches_oracle(O, results[i], work[i][0], work[i][1], 31, 5, 0.02, int(work[i][2]))
