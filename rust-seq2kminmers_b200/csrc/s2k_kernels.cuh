@@ -381,7 +381,22 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             S.qmap[m >> 6] = (uint16_t)(m < q + clo ? 2 * tid : 2 * tid + 1);
 
         // ---- S4: compaction (predicated byte stores in HPC order)
-        {
+        if (!HPC && (klo & khi) == 0xffffffffu && ((XB + q) & 15u) == 0) {
+            // every base kept (no HPC): byte stores would advance at a 64-byte lane stride = 16-way bank conflicts.
+            // Pack the 64 classes and store four 16-byte vectors instead.
+            uint4 *cp4 = reinterpret_cast<uint4 *>(S.code + XB + q);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                uint32_t o4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t x = w[4 * v + i];
+                    o4[i] = (uint32_t)S.lut[x & 0xffu] | ((uint32_t)S.lut[(x >> 8) & 0xffu] << 8) |
+                            ((uint32_t)S.lut[(x >> 16) & 0xffu] << 16) | ((uint32_t)S.lut[x >> 24] << 24);
+                }
+                cp4[v] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            }
+        } else {
             uint8_t *cp = S.code + XB + q;
 #pragma unroll
             for (int b = 0; b < 64; ++b) {
