@@ -285,10 +285,26 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         assert split_one or out.n_items == n_items
+        h2d_actual, n_packed, n_plain = ctx.last_transport()
         e2e = {"value": (L if split_one else world * n_bases) * e_steps / float(tt.item()) / 1e9, "unit": "Gbp/s",
-               "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
-               "d2h_bytes_per_step": 17 * n_items + 8 * (n_reads + 1) * 2 + 4 * n_reads,
-               "steps": e_steps, "api": "s2k_run (C ABI, pinned host buffers)"}
+               "h2d_bytes_per_step": int(h2d_actual),
+               "host_input_bytes_per_step": n_bases + 8 * (n_reads + 1),
+               "d2h_bytes_per_step": 17 * int(out.n_items) + 8 * (n_reads + 1) * 2 + 4 * n_reads,
+               "steps": e_steps, "api": "s2k_run (C ABI, pinned host ASCII buffers in, pinned host items out)",
+               "transport": f"{n_packed} slabs packed to 2 bits/base by host threads + {n_plain} slabs as plain ASCII (s2k_ctx_set_transport default)"}
+        # the same with the 2-bit transport switched off: every byte crosses PCIe as ASCII
+        ctx.set_transport(0, 0.0)
+        ctx.run(hb_np, hso_np, L_PARAM, K_PARAM, DENSITY, S.HashMode(mode), S.HashVariant(variant), copy=False, no_tail_rule=split_one)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ctx.run(hb_np, hso_np, L_PARAM, K_PARAM, DENSITY, S.HashMode(mode), S.HashVariant(variant), copy=False, no_tail_rule=split_one)
+        torch.cuda.synchronize()
+        tt2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+        e2e["plain_ascii_transport_value"] = (L if split_one else world * n_bases) * 2 / float(tt2.item()) / 1e9
+        ctx.set_transport(0, 0.7)
         del hb, hso
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)

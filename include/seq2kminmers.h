@@ -141,6 +141,15 @@ int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes);
 int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_params *params, s2k_result *out);
 int s2k_last_fastx(const s2k_ctx *ctx, uint64_t *n_seqs, uint64_t *n_bases, const uint8_t **bases, const uint64_t **seq_off);
 
+/* Transport of large host batches (s2k_run, s2k_run_fastx).  PCIe, not the GPU, bounds the end-to-end rate, so a share
+ * `pack_ratio` of the slabs (default 0.7; 0 = never) is packed to 2 bits per base by `host_threads` host threads
+ * (default 0 = min(16, hardware threads); AVX-512) into pinned staging, copied and unpacked on the device, while the
+ * remaining slabs travel as plain ASCII so that both the packers and PCIe stay busy.  Results are identical: a slab
+ * holding any byte other than upper-case A/C/G/T always travels as ASCII. */
+int s2k_ctx_set_transport(s2k_ctx *ctx, int host_threads, double pack_ratio);
+/* Last s2k_run / s2k_run_fastx: bytes actually copied host -> device, slabs that travelled packed / as ASCII. */
+int s2k_last_transport(const s2k_ctx *ctx, uint64_t *h2d_bytes, uint64_t *packed_slabs, uint64_t *plain_slabs);
+
 /* Same, DEVICE buffers already resident in HBM (bases 16-byte aligned); results stay on the device.
  * `stream` is a cudaStream_t (NULL = the context's own stream).  Returns after the launch sequence has been
  * enqueued and the two scalar totals have been read back (one stream synchronisation). */

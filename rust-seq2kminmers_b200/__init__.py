@@ -81,7 +81,8 @@ ABI_SYMBOLS = (
     "s2k_ctx_create", "s2k_ctx_destroy", "s2k_ctx_set_flags", "s2k_run", "s2k_run_device", "s2k_encode_rle",
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
-    "s2k_ctx_set_slab_bytes", "s2k_last_kernel_kind", "s2k_run_fastx", "s2k_last_fastx",
+    "s2k_ctx_set_slab_bytes", "s2k_last_kernel_kind", "s2k_run_fastx", "s2k_last_fastx", "s2k_ctx_set_transport",
+    "s2k_last_transport",
 )
 
 
@@ -126,6 +127,10 @@ class Library:
         L.s2k_ctx_set_timing.argtypes = [vp, C.c_int]
         L.s2k_ctx_set_slab_bytes.restype = C.c_int
         L.s2k_ctx_set_slab_bytes.argtypes = [vp, C.c_uint64]
+        L.s2k_last_transport.restype = C.c_int
+        L.s2k_last_transport.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.s2k_ctx_set_transport.restype = C.c_int
+        L.s2k_ctx_set_transport.argtypes = [vp, C.c_int, C.c_double]
         L.s2k_run_fastx.restype = C.c_int
         L.s2k_run_fastx.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(_Params), C.POINTER(_Result)]
         L.s2k_last_fastx.restype = C.c_int
@@ -339,6 +344,16 @@ class Context:
     def set_slab_bytes(self, nbytes: int):
         """Target slab size of the pipelined host path (0 = default 256 MiB)."""
         self._check(self.lib.c.s2k_ctx_set_slab_bytes(self.h, int(nbytes)))
+
+    def set_transport(self, host_threads: int = 0, pack_ratio: float = 0.7):
+        """2-bit transport of large host batches: share of slabs packed by host threads (0 = plain ASCII only)."""
+        self._check(self.lib.c.s2k_ctx_set_transport(self.h, int(host_threads), float(pack_ratio)))
+
+    def last_transport(self):
+        """(bytes copied host->device, slabs packed, slabs plain) of the last host-buffer run."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.c.s2k_last_transport(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def set_timing(self, enabled: bool):
         self._check(self.lib.c.s2k_ctx_set_timing(self.h, 1 if enabled else 0))

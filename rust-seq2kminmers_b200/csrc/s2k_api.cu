@@ -106,6 +106,11 @@ struct s2k_ctx {
     bool pipe_ready = false;
     uint64_t slab_bytes = 0;        // 0 = default
     Buf d_in[2], d_in_off[2], h_off_stage[2];
+    Buf d_pack[2], h_pack[3];       // 2-bit transport: device landing buffers, ring of pinned staging buffers
+    cudaEvent_t ev_pack[3] = {nullptr, nullptr, nullptr};
+    int host_threads = 0;           // 0 = min(16, hardware threads)
+    double pack_ratio = 0.7;        // share of slabs that travel packed (the rest keep PCIe busy with plain ASCII)
+    uint64_t tr_h2d_bytes = 0, tr_packed = 0, tr_plain = 0;   // last s2k_run: bytes copied to the device, slabs by kind
     Buf h_fx_bases, h_fx_off;       // s2k_run_fastx: parsed file in pinned memory
     uint64_t fx_n_seqs = 0, fx_n_bases = 0;
 };
@@ -170,6 +175,62 @@ void release(Buf &b)
 
 } // namespace
 #include "s2k_fastx.inc"
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+#include <atomic>
+namespace {
+
+// ---- 2-bit transport: host side.  Packs n bases (4 per byte, code (b>>1)&3: A0 C1 T2 G3) and counts the bytes that
+// are not upper-case A/C/G/T; a slab with any such byte travels as plain ASCII instead, so nothing is ever lost.
+bool host_has_avx512()
+{
+#if defined(__x86_64__)
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+#else
+    return false;
+#endif
+}
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw,avx512vl")))
+uint64_t pack2_avx512(const uint8_t *src, uint8_t *dst, size_t n)      // n multiple of 64
+{
+    const __m512i three = _mm512_set1_epi8(3);
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i m1 = _mm512_set1_epi16(0x0401), m2 = _mm512_set1_epi32(0x00100001);
+    uint64_t bad = 0;
+    for (size_t i = 0; i < n; i += 64) {
+        const __m512i v = _mm512_loadu_si512(src + i);
+        const __m512i c = _mm512_and_si512(_mm512_srli_epi16(v, 1), three);
+        bad += (uint64_t)__builtin_popcountll(_mm512_cmpneq_epi8_mask(_mm512_shuffle_epi8(lut, c), v));
+        const __m512i p32 = _mm512_madd_epi16(_mm512_maddubs_epi16(c, m1), m2);     // c0 + 4 c1 + 16 c2 + 64 c3 per 4 bases
+        _mm_storeu_si128((__m128i *)(dst + (i >> 2)), _mm512_cvtepi32_epi8(p32));
+    }
+    return bad;
+}
+#endif
+uint64_t pack2_range(const uint8_t *src, uint8_t *dst, size_t lo, size_t hi)   // lo multiple of 64; packs bases [lo, hi)
+{
+    uint64_t bad = 0;
+    size_t i = lo;
+#if defined(__x86_64__)
+    const size_t body = (hi - lo) & ~size_t(63);
+    bad += pack2_avx512(src + lo, dst + (lo >> 2), body);
+    i = lo + body;
+#endif
+    for (; i < hi; i += 4) {
+        uint8_t o = 0;
+        for (size_t j = 0; j < 4 && i + j < hi; ++j) {
+            const uint8_t b = src[i + j], c = (b >> 1) & 3;
+            bad += "ACTG"[c] != b;
+            o |= (uint8_t)(c << (2 * j));
+        }
+        dst[i >> 2] = o;
+    }
+    return bad;
+}
+
+} // namespace
 namespace {
 
 struct Plan {
@@ -570,7 +631,8 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
                   &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in_off[0], &ctx->d_in_off[1],
-                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_fx_bases, &ctx->h_fx_off};
+                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1],
+                  &ctx->h_pack[0], &ctx->h_pack[1], &ctx->h_pack[2]};
     for (Buf *b : all) release(*b);
     if (ctx->tm.created) {
         for (auto &e : ctx->tm.ev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
@@ -580,6 +642,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
         cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_free[i]); }
         cudaEventDestroy(ctx->ev_out); cudaEventDestroy(ctx->ev_done);
+        for (int i = 0; i < 3; ++i) cudaEventDestroy(ctx->ev_pack[i]);
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -653,6 +716,24 @@ int s2k_run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_o
     return run_device(ctx, d_bases, d_seq_off, n_seqs, n_bases, P, st, out);
 }
 
+int s2k_ctx_set_transport(s2k_ctx *ctx, int host_threads, double pack_ratio)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (host_threads < 0 || host_threads > 256 || !(pack_ratio >= 0.0 && pack_ratio <= 1.0)) return fail(ctx, S2K_ERR_BAD_PARAM, "bad transport setting");
+    ctx->host_threads = host_threads;
+    ctx->pack_ratio = pack_ratio;
+    return S2K_OK;
+}
+
+int s2k_last_transport(const s2k_ctx *ctx, uint64_t *h2d_bytes, uint64_t *packed_slabs, uint64_t *plain_slabs)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (h2d_bytes) *h2d_bytes = ctx->tr_h2d_bytes;
+    if (packed_slabs) *packed_slabs = ctx->tr_packed;
+    if (plain_slabs) *plain_slabs = ctx->tr_plain;
+    return S2K_OK;
+}
+
 int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes)
 {
     if (!ctx) return S2K_ERR_NULL;
@@ -672,6 +753,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
         CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) { CU(cudaEventCreate(&ctx->ev_in[i])); CU(cudaEventCreate(&ctx->ev_free[i])); }
         CU(cudaEventCreate(&ctx->ev_out)); CU(cudaEventCreate(&ctx->ev_done));
+        for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&ctx->ev_pack[i]));
         ctx->pipe_ready = true;
     }
     cudaStream_t st = ctx->stream;
@@ -699,11 +781,82 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     if ((rc = ensure(ctx, ctx->h_min_off, (n_seqs + 1) * 8, true))) return rc;
     if ((rc = ensure(ctx, ctx->h_min_cnt, std::max<uint64_t>(n_seqs, 1) * 4, true))) return rc;
 
+    // ---- 2-bit transport: a share of the slabs is packed 4 bases/byte by host threads (pinned ring of 3 staging
+    // buffers), copied (a quarter of the bytes) and unpacked on the device; the other slabs go as plain ASCII so that
+    // PCIe and the packers work at the same time.  A slab with any byte outside upper-case ACGT goes as ASCII.
+    int T = ctx->host_threads > 0 ? ctx->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const bool can_pack = host_has_avx512() && ctx->pack_ratio > 0.0 && n_slabs >= 3;
+    std::vector<int> ps_of(n_slabs, -1);
+    std::vector<size_t> packed_slabs;
+    if (can_pack) {
+        double acc = 0.0;
+        for (size_t s = 0; s < n_slabs; ++s) {
+            acc += std::min(1.0, ctx->pack_ratio);
+            if (acc >= 1.0 - 1e-9) { acc -= 1.0; ps_of[s] = (int)packed_slabs.size(); packed_slabs.push_back(s); }
+        }
+    }
+    const size_t np = packed_slabs.size();
+    if (np) {
+        for (int i = 0; i < 2; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
+        for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->h_pack[i], max_b / 4 + 64, true))) return rc;
+    }
+    std::vector<std::atomic<uint32_t>> pk_done(np);
+    std::vector<std::atomic<uint64_t>> pk_bad(np);
+    for (size_t i = 0; i < np; ++i) { pk_done[i].store(0); pk_bad[i].store(0); }
+    std::vector<int> pk_state(np, 0);                      // 0 pending, 1 copy issued (ev_pack recorded), 2 buffer not used
+    std::atomic<int64_t> pk_released{0};                   // staging buffers of packed slabs [0, released) are free again
+    std::atomic<bool> pk_abort{false};
+    struct Joiner {
+        std::vector<std::thread> th; std::atomic<bool> *abort;
+        ~Joiner() { abort->store(true); for (auto &t : th) t.join(); }
+    } joiner{{}, &pk_abort};
+    if (np) {
+        for (int wi = 0; wi < T; ++wi)
+            joiner.th.emplace_back([&, wi]() {
+                for (size_t ps = 0; ps < np; ++ps) {
+                    while ((int64_t)ps >= pk_released.load(std::memory_order_acquire) + 3) {
+                        if (pk_abort.load()) return;
+                        std::this_thread::yield();
+                    }
+                    const size_t sl = packed_slabs[ps];
+                    const uint64_t b0 = seq_off[cut[sl]], nb = seq_off[cut[sl + 1]] - b0;
+                    const uint64_t chunk = ((nb + T - 1) / T + 63) & ~uint64_t(63);
+                    const uint64_t lo = std::min<uint64_t>(nb, chunk * wi), hi = std::min<uint64_t>(nb, lo + chunk);
+                    if (hi > lo) pk_bad[ps].fetch_add(pack2_range(bases + b0, ptr<uint8_t>(ctx->h_pack[ps % 3]), lo, hi));
+                    pk_done[ps].fetch_add(1, std::memory_order_release);
+                }
+            });
+    }
+    auto poll_release = [&]() {
+        int64_t r = pk_released.load();
+        while ((size_t)r < np && (pk_state[r] == 2 || (pk_state[r] == 1 && cudaEventQuery(ctx->ev_pack[r % 3]) == cudaSuccess))) ++r;
+        pk_released.store(r, std::memory_order_release);
+    };
+
     auto issue_h2d = [&](size_t s) -> int {
         const int b = (int)(s & 1);
         const uint64_t r0 = cut[s], r1 = cut[s + 1], nb = seq_off[r1] - seq_off[r0];
+        const int ps = ps_of[s];
+        bool packed = false;
+        if (ps >= 0) {
+            while (pk_done[ps].load(std::memory_order_acquire) < (uint32_t)T) { poll_release(); std::this_thread::yield(); }
+            packed = nb > 0 && pk_bad[ps].load() == 0;
+        }
         CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_free[b], 0));          // the kernels of slab s-2 are done with it
-        if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, bases + seq_off[r0], nb, cudaMemcpyHostToDevice, ctx->s_h2d));
+        ctx->tr_h2d_bytes += (packed ? (nb + 3) / 4 : nb) + (r1 - r0 + 1) * 8;
+        if (packed) ++ctx->tr_packed; else ++ctx->tr_plain;
+        if (packed) {
+            CU(cudaMemcpyAsync(ctx->d_pack[b].p, ctx->h_pack[ps % 3].p, (nb + 3) / 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CU(cudaEventRecord(ctx->ev_pack[ps % 3], ctx->s_h2d));
+            pk_state[ps] = 1;
+            const int g = (int)std::min<uint64_t>((nb / 16 + 256) / 256, (uint64_t)ctx->sm_count * 8);
+            S2K_LAUNCH(k_unpack2, g, 256, 0, ctx->s_h2d, false, ptr<uint32_t>(ctx->d_pack[b]), nb, ptr<uint8_t>(ctx->d_in[b]));
+            ctx->launches += 1;
+        } else {
+            if (ps >= 0) pk_state[ps] = 2;
+            if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, bases + seq_off[r0], nb, cudaMemcpyHostToDevice, ctx->s_h2d));
+        }
+        poll_release();
         // offsets: copy the caller's slice as it is, rebase it to the slab on the device
         uint64_t *d_off = ptr<uint64_t>(ctx->d_in_off[b]);
         CU(cudaMemcpyAsync(d_off, seq_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
@@ -718,6 +871,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     };
 
     uint64_t items = 0, mins = 0;
+    ctx->tr_h2d_bytes = 0; ctx->tr_packed = 0; ctx->tr_plain = 0;
     CU(cudaEventRecord(ctx->ev_free[0], st));
     CU(cudaEventRecord(ctx->ev_free[1], st));
     CU(cudaEventRecord(ctx->ev_out, ctx->s_d2h));
@@ -777,6 +931,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_mins) + mins * 16, dev.minimizers, nm * 16, cudaMemcpyDeviceToHost, so));
         CU(cudaEventRecord(ctx->ev_out, so));
         items += ni; mins += nm;
+        poll_release();
     }
     CU(cudaStreamSynchronize(ctx->s_d2h));
     CU(cudaStreamSynchronize(ctx->s_h2d));
@@ -816,6 +971,7 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
     if ((rc = ensure(ctx, ctx->d_seq_off, (n_seqs + 1) * 8, false))) return rc;
     if (n_bases) CU(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->d_seq_off.p, seq_off, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    ctx->tr_h2d_bytes = n_bases + (n_seqs + 1) * 8; ctx->tr_packed = 0; ctx->tr_plain = 1;
     s2k_result dev;
     rc = run_device(ctx, ptr<uint8_t>(ctx->d_bases), ptr<uint64_t>(ctx->d_seq_off), n_seqs, n_bases, P, st, &dev);
     if (rc != S2K_OK) return rc;

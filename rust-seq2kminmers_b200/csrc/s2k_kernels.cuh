@@ -1001,6 +1001,26 @@ __global__ void k_add_seq(uint4 *__restrict__ mins, uint64_t n, uint32_t add)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mins[i].w += add;
 }
 
+// 2-bit transport (s2k_run): the host packs ACGT-only slabs 4 bases per byte (base i in bits 2*(i%4), code = (b>>1)&3:
+// A0 C1 T2 G3) to quarter the PCIe traffic; this kernel restores the ASCII bytes the rest of the path works on.
+__global__ void __launch_bounds__(256) k_unpack2(const uint32_t *__restrict__ packed, uint64_t n_bases, uint8_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nvec = (n_bases + 15) / 16;                    // 16 bases = one packed word = one 16-byte store
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint32_t pw = packed[v];
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x |= ((0x47544341u >> (8 * ((pw >> (8 * i + 2 * j)) & 3u))) & 0xffu) << (8 * j);   // "ACTG"
+            w[i] = x;
+        }
+        *reinterpret_cast<uint4 *>(out + 16 * v) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ synthetic reads
 // Workload generator of SURVEY.md 8(d): 32 bases per 64-bit word, word(j) = splitmix64 finalizer of
 // seed + (j+1)*0x9E3779B97F4A7C15, base(i) = "ACGT"[(word(i>>5) >> 2*(i&31)) & 3].  Same data on host

@@ -63,14 +63,20 @@ def test_error_codes_mirror_reference_panics(S, emu_ctx):
 
 def test_pipelined_host_path_emulated(S, O, emu_ctx, batches):
     """s2k_run on a batch larger than 1.5 slabs: slabs cut at sequence boundaries, offsets and sequence indices stitched."""
-    bases, so = batches.batch([9000, 150, 0, 20000, 31, 7000, 0, 0, 12000, 150, 150, 30000, 5])
+    seqs = [batches.seq(n) for n in [9000, 150, 0, 20000, 31, 7000, 0, 0, 12000, 150, 150, 30000, 5, 9000, 9000]]
+    seqs[8] = batches.seq(12000, alphabet=b"ACGTN")       # a slab with non-ACGT bytes must travel as ASCII
+    seqs[13] = batches.seq(9000, alphabet=b"ACGTacgt")
+    bases, so = batches.pack(seqs)
     emu_ctx.set_slab_bytes(10000)
     try:
-        for mode in (S.HashMode.HpcSimd, S.HashMode.Regular):
-            got = emu_ctx.run(bases, so, 31, 3, 0.03, mode, want_minimizers=True)
-            assert_batch_matches_oracle(O, got, bases, so, 31, 3, 0.03, mode)
+        for ratio in (0.7, 1.0, 0.0):                     # 2-bit transport for 70 % / all / none of the slabs
+            emu_ctx.set_transport(3, ratio)
+            for mode in (S.HashMode.HpcSimd, S.HashMode.Regular):
+                got = emu_ctx.run(bases, so, 31, 3, 0.03, mode, want_minimizers=True)
+                assert_batch_matches_oracle(O, got, bases, so, 31, 3, 0.03, mode)
     finally:
         emu_ctx.set_slab_bytes(0)
+        emu_ctx.set_transport(0, 0.7)
 
 
 def test_random_parameter_fuzz_emulated(S, O, emu_ctx, batches):

@@ -161,14 +161,20 @@ def test_cpp_host_wrapper_twin_of_reference_test(S, tmp_path):
 def test_pipelined_host_path(S, O, gpu_ctx, batches):
     """s2k_run streaming a batch through the device in many small slabs (three streams) == the oracle."""
     lens = [9000, 150, 0, 20000, 31, 7000, 0, 0, 12000, 150, 150, 30000, 5] * 6
-    bases, so = batches.batch(lens)
+    seqs = [batches.seq(n) for n in lens]
+    seqs[8] = batches.seq(12000, alphabet=b"ACGTN")       # slabs with non-ACGT bytes must travel as ASCII
+    seqs[40] = batches.seq(7000, alphabet=b"ACGTacgt")
+    bases, so = batches.pack(seqs)
     gpu_ctx.set_slab_bytes(40000)
     try:
-        for mode in (S.HashMode.HpcSimd, S.HashMode.Hpc, S.HashMode.Simd):
-            got = gpu_ctx.run(bases, so, 31, 3, 0.03, mode, want_minimizers=True)
-            assert_batch_matches_oracle(O, got, bases, so, 31, 3, 0.03, mode)
+        for ratio, threads in ((0.7, 0), (1.0, 5), (0.0, 0)):   # 2-bit transport for 70 % / all / none of the slabs
+            gpu_ctx.set_transport(threads, ratio)
+            for mode in (S.HashMode.HpcSimd, S.HashMode.Hpc, S.HashMode.Simd):
+                got = gpu_ctx.run(bases, so, 31, 3, 0.03, mode, want_minimizers=True)
+                assert_batch_matches_oracle(O, got, bases, so, 31, 3, 0.03, mode)
     finally:
         gpu_ctx.set_slab_bytes(0)
+        gpu_ctx.set_transport(0, 0.7)
 
 
 def test_one_sequence_split_across_ranks(S, O, gpu_ctx):
