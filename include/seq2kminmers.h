@@ -143,7 +143,7 @@ int s2k_last_fastx(const s2k_ctx *ctx, uint64_t *n_seqs, uint64_t *n_bases, cons
 
 /* Transport of large host batches (s2k_run, s2k_run_fastx).  PCIe, not the GPU, bounds the end-to-end rate, so a share
  * `pack_ratio` of the slabs (default 0.7; 0 = never) is packed to 2 bits per base by `host_threads` host threads
- * (default 0 = min(16, hardware threads); AVX-512) into pinned staging, copied and unpacked on the device, while the
+ * (default 0 = 3/4 of the hardware threads, at most 16; AVX-512) into pinned staging, copied and unpacked on the device, while the
  * remaining slabs travel as plain ASCII so that both the packers and PCIe stay busy.  Results are identical: a slab
  * holding any byte other than upper-case A/C/G/T always travels as ASCII. */
 int s2k_ctx_set_transport(s2k_ctx *ctx, int host_threads, double pack_ratio);
