@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 
     for (int i = tid; i < 256; i += NT) S.lut[i] = A.cls_lut[i];
     if (tid < XYN) S.xy[tid] = A.xy[tid];
-    for (int i = tid; i < XB + WIN + 128; i += NT) S.code[i] = ZC8;
+    for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
     for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
     for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
     if (tid == 0) { S.n_dirty[0] = 0; S.n_dirty[1] = 0; }
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 #pragma unroll
             for (int b = 0; b < 64; ++b) {
                 const uint32_t kb = (b < 32 ? (klo >> b) : (khi >> (b - 32))) & 1u;
-                if (kb) { *cp = S.lut[(w[b >> 2] >> (8 * (b & 3))) & 0xffu]; ++cp; }
+                if (kb) { *cp = S.lut[__byte_perm(w[b >> 2], 0u, 0x4440u + (b & 3))]; ++cp; }
             }
         }
         __syncthreads();

@@ -128,6 +128,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
     emu::blk->wbar[w]->arrive_and_wait();
     return r;
 }
+static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
