@@ -108,8 +108,8 @@ typedef struct s2k_ctx s2k_ctx;
 
 /* Flags for s2k_ctx_set_flags. */
 #define S2K_WANT_MINIMIZERS 1u  /* s2k_run (host) also copies the minimizer stream back */
-#define S2K_GENERAL_KERNEL  4u  /* only meaningful in builds with -DS2K_FAST=1 (an experiment, off by default): use the
-                                   general minimizer kernel even where the raw-space variant applies; results identical */
+#define S2K_GENERAL_KERNEL  4u  /* accepted and ignored: there is one minimizer kernel (an earlier raw-space variant that
+                                   this flag bypassed was measured slower and removed) */
 #define S2K_DEBUG_TINY_CAP  8u  /* tests only: start with room for 1000 minimizers so that the grow-and-rerun path runs */
 #define S2K_NO_TAIL_RULE    2u  /* do not apply the `(len-l+1) % 16 == 0` tail rule of src/nthash_avx512_32.rs:134-138:
                                    for callers that process one sequence in pieces (sharding.py) and apply the rule
@@ -190,8 +190,8 @@ const char *s2k_strerror(int status);
 int s2k_abi_version(void);
 /* Kernels launched by the context since creation (for benchmark bookkeeping). */
 uint64_t s2k_launch_count(const s2k_ctx *ctx);
-/* Which minimizer kernel the last run used: 0 = k_minimizers (always, in default builds); in -DS2K_FAST=1 builds
- * 1 = k_minimizers_fast, 2 = it declined (non-ACGT bases, long homopolymers, dense selection) and k_minimizers reran. */
+/* Which minimizer kernel the last run used: always 0 = k_minimizers (values 1 and 2 belonged to a raw-space variant
+ * that was measured slower and removed; the entry point stays for ABI stability). */
 int s2k_last_kernel_kind(const s2k_ctx *ctx);
 /* Name and average duration (ms) of the context's dominant kernel over the last s2k_run_device call,
  * measured with CUDA events on the launching stream when timing is enabled. */

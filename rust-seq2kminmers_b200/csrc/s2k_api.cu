@@ -16,12 +16,6 @@
 using namespace s2k;
 
 // Build-time experiments, both bit-exact and both measured SLOWER than k_minimizers on B200:
-#ifndef S2K_WARP
-#define S2K_WARP 0                  // 1: k_minimizers_w (warp-independent sub-tiles) replaces k_minimizers
-#endif
-#ifndef S2K_FAST
-#define S2K_FAST 0                  // 1: try k_minimizers_fast (raw-space rolling, register FIFO) first, fall back when it declines
-#endif
 
 // Kernel launch.  `conc` only matters to the test-tier host emulation (tests/emu): kernels with static shared
 // state run their blocks one after the other there.
@@ -99,7 +93,7 @@ struct s2k_ctx {
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
     bool attr_set = false;
-    int kernel_kind = 0;            // last run: 0 general kernel, 1 fast kernel, 2 fast kernel declined -> general
+    int kernel_kind = 0;            // last run: always 0 (one minimizer kernel); kept for ABI stability
     // pipelined host path (s2k_run on large batches)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_out = nullptr, ev_done = nullptr;
@@ -237,8 +231,6 @@ struct Plan {
     bool hpc, simd, w31, quirk;
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
-    bool fast_ok;    // k_minimizers_fast covers this plan (HPC mode, 20 <= l <= 31, moderate density)
-    uint32_t fh0, rh0, hcap;
     uint8_t lut[256];   // raw byte -> code of its base class
     uint2 xy[XYN];
 };
@@ -262,14 +254,8 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     P.d = (p->mode == S2K_MODE_HPC) ? 1u : 0u;       // Hpc: the l-mer is emitted when the NEXT kept base shows up
     P.need = P.l - 1 + P.d;
     P.quirk = P.simd && !P.w31 && !(ctx && (ctx->flags & S2K_NO_TAIL_RULE));
-#if S2K_WARP
-    // warp-tile kernel: per-warp halo of 64 raw bases when that almost surely holds l-1(+1) kept bases, else 256
-    P.halo = (P.hpc ? P.need <= 31 : P.need <= 64) ? 64u : 256u;
-    P.tile = (uint32_t)WTILE;
-#else
     P.halo = P.need >= 128 ? 512u : 256u;
     P.tile = P.hpc ? (uint32_t)WIN - P.halo : std::min<uint32_t>((uint32_t)CAP, (uint32_t)WIN - P.halo);
-#endif
     const uint32_t bs = bound_scalar(p->density);
     uint64_t excl;                                   // select iff hash < excl
     if (P.simd) { uint32_t b = bound_simd(bs); if (P.w31) b /= 2; excl = b; }
@@ -293,15 +279,6 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         P.lut['A'] = code_of[0]; P.lut['C'] = code_of[1]; P.lut['G'] = code_of[2]; P.lut['T'] = code_of[3];
         P.lut['N'] = code_of[4];
     }
-    {   // raw-space fast kernel: initial state = l bases 'A' (FIFO of zeros), hit list sized from the selection rate
-        P.fh0 = P.rh0 = 0;
-        for (uint32_t i = 0; i < P.l; ++i) { P.fh0 ^= rolw(h[0], i, w); P.rh0 ^= rolw(rc[0], i, w); }
-        const double frac = P.none ? 0.0 : std::min(1.0, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
-        const double mean = 256.0 * std::min(1.0, 2.0 * frac);
-        const double want = 4.0 * mean + 16.0;
-        P.hcap = (uint32_t)std::min(128.0, std::max(16.0, want));
-        P.fast_ok = S2K_FAST && P.hpc && P.l >= 20 && P.l <= 31 && want <= 128.0 && !(ctx && (ctx->flags & S2K_GENERAL_KERNEL));
-    }
     std::memset(P.xy, 0, sizeof(P.xy));
     for (int o = 0; o < 6; ++o)
         for (int i = 0; i < 6; ++i) {
@@ -323,13 +300,6 @@ int set_attrs(s2k_ctx *ctx)
     CU(cudaFuncSetAttribute(k_minimizers<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_minimizers<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(k_minimizers<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(k_minimizers_fast<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
-    CU(cudaFuncSetAttribute(k_minimizers_fast<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
-    CU(cudaFuncSetAttribute(k_minimizers_fast<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
-    CU(cudaFuncSetAttribute(k_minimizers_w<false, false, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<68>)));
-    CU(cudaFuncSetAttribute(k_minimizers_w<false, true, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<68>)));
-    CU(cudaFuncSetAttribute(k_minimizers_w<true, false, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<52>)));
-    CU(cudaFuncSetAttribute(k_minimizers_w<true, true, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<52>)));
     ctx->attr_set = true;
     return S2K_OK;
 }
@@ -392,40 +362,18 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         if (ctx->flags & S2K_DEBUG_TINY_CAP) cap = std::min<uint64_t>(cap, 1000);
     }
 
-    // Two minimizer kernels with identical outputs: k_minimizers_fast (raw-space rolling, register FIFO) for the plans
-    // it covers, k_minimizers for everything else and whenever the fast one declines (ERR_FAST).
-    bool use_fast = P.fast_ok;
     uint32_t n_tiles = 0, tile_eff = 0;
     ctx->kernel_kind = 0;
     for (int attempt = 0;; ++attempt) {
         if (attempt == 4) return fail(ctx, S2K_ERR_INTERNAL, "minimizer kernel did not converge");
-        tile_eff = use_fast ? (uint32_t)FTILE : P.tile;
+        tile_eff = P.tile;
         const uint64_t n_tiles64 = (n_bases + tile_eff - 1) / tile_eff;
         if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
         n_tiles = (uint32_t)n_tiles64;
-        int max_grid;
-        size_t hscr_words, smem;
-        void (*kfn)(const K1Args);
-        if (use_fast) {
-            max_grid = ctx->sm_count * 4;
-            hscr_words = (size_t)max_grid * NT * 2 * P.hcap;
-            smem = sizeof(SmemF);
-            kfn = P.w31 ? k_minimizers_fast<true, 0> : (P.d ? k_minimizers_fast<false, 1> : k_minimizers_fast<false, 0>);
-        } else {
-#if S2K_WARP
-            max_grid = ctx->sm_count * 3;
-            hscr_words = (size_t)max_grid * 8 * HSW;
-            smem = P.hpc ? sizeof(SmemW<52>) : sizeof(SmemW<68>);
-            kfn = P.hpc ? (P.w31 ? k_minimizers_w<true, true, 52> : k_minimizers_w<true, false, 52>)
-                        : (P.w31 ? k_minimizers_w<false, true, 68> : k_minimizers_w<false, false, 68>);
-#else
-            max_grid = ctx->sm_count * S2K_MINB;
-            hscr_words = (size_t)max_grid * WIN;
-            smem = sizeof(Smem);
-            kfn = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
-                        : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
-#endif
-        }
+        const int max_grid = ctx->sm_count * S2K_MINB;
+        const size_t hscr_words = (size_t)max_grid * WIN, smem = sizeof(Smem);
+        void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
+                                          : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
         if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;
@@ -444,7 +392,6 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.err = reinterpret_cast<uint32_t *>(small + 5);
         A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
         A.tile = tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
-        A.fast_fh0 = P.fh0; A.fast_rh0 = P.rh0; A.fast_hcap = P.hcap;
         std::memcpy(A.cls_lut, P.lut, 256);
         std::memcpy(A.xy, P.xy, sizeof(P.xy));
         CU(cudaMemsetAsync(small, 0, 64, st));
@@ -461,12 +408,6 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         CU(cudaMemcpyAsync(hsmall, small, 8, cudaMemcpyDeviceToHost, st));          // record cursor == total minimizers
         CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (use_fast && ((uint32_t)hsmall[2] & ERR_FAST)) {   // outside the fast kernel's model: redo with the general one
-            use_fast = false;
-            ctx->kernel_kind = 2;
-            continue;
-        }
-        if (use_fast) ctx->kernel_kind = 1;
         n_min = hsmall[0];
         if (n_min <= cap) break;
         cap = n_min;                                   // exact size known now: rerun once

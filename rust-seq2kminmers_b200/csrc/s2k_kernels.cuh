@@ -90,7 +90,6 @@ struct K1Args {
     uint64_t  n_seqs, n_bases;
     uint32_t  n_tiles, tile, halo;
     uint32_t  l, d, need, thr;
-    uint32_t  fast_fh0, fast_rh0, fast_hcap;   // k_minimizers_fast: hash state of l bases 'A', hit-list capacity per thread
     uint8_t   cls_lut[256];      // raw byte -> 8 * base class (classes 0..5)
     uint2     xy[XYN];           // byte offset 4*code(out)+code(in) -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
 };
@@ -610,10 +609,6 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     }
 }
 
-} // namespace s2k
-#include "s2k_kernel_warp.cuh"
-#include "s2k_kernel_fast.cuh"
-namespace s2k {
 
 // ------------------------------------------------------------------------------------------------ tile order
 // k_minimizers leaves each tile's records contiguous but the tiles in completion order.  Two-level exclusive prefix

@@ -85,33 +85,6 @@ def test_random_parameter_fuzz_emulated(S, O, emu_ctx, batches):
         assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
 
 
-@pytest.mark.parametrize("define", ["-DS2K_WARP=1", "-DS2K_FAST=1"])
-def test_experimental_kernels_stay_exact(S, O, batches, fixture_seq, tmp_path, define):
-    """The two build-time experiments (warp-tile kernel, raw-space kernel with decline-and-rerun) must keep producing
-    the oracle's results; they are not part of the default build."""
-    import subprocess
-    from conftest import ROOT
-    lib = tmp_path / "libs2k_emu_x.so"
-    subprocess.run(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-DS2K_EMU", define, f"-I{ROOT / 'tests' / 'emu'}",
-                    "-x", "c++", str(ROOT / "rust-seq2kminmers_b200" / "csrc" / "s2k_api.cu"), "-o", str(lib)], check=True)
-    ctx = S.Context(0, S.Library(lib))
-    try:
-        kinds = set()
-        parts = [fixture_seq[:70000], batches.seq(150), batches.seq(0), batches.seq(31), batches.seq(9000, runp=0.6),
-                 batches.seq(3000, alphabet=b"ACGTN"), batches.seq(40000)]
-        bases, so = batches.pack(parts)
-        clean, so_clean = batches.pack([fixture_seq[:70000], batches.seq(150), batches.seq(20000)])
-        for (b, o) in ((bases, so), (clean, so_clean)):
-            for (l, k, d, mode, var) in [(31, 5, 0.02, 3, 0), (31, 5, 0.02, 1, 0), (25, 3, 0.02, 3, 1), (31, 5, 0.02, 2, 0), (12, 2, 0.05, 3, 0)]:
-                got = ctx.run(b, o, l, k, d, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)
-                kinds.add(ctx.last_kernel_kind)
-                assert_batch_matches_oracle(O, got, b, o, l, k, d, mode, var)
-        if define == "-DS2K_FAST=1":
-            assert kinds == {0, 1, 2}      # general (non-HPC / short l), fast, fast declined -> general
-    finally:
-        ctx.close()
-
-
 def test_capacity_overflow_reruns_emulated(S, O, emu_ctx, batches):
     """The minimizer buffer is sized from the expected selection rate; when a batch is denser the kernel reports the
     exact count and the host reruns once with that size.  Forced here with a 1000-record start capacity."""
