@@ -232,7 +232,7 @@ struct Plan {
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
     uint8_t lut[256];   // raw byte -> code of its base class
-    uint2 xy[XYN];
+    uint2 xy[XYN], xf[XFN], x2[XFN];
 };
 
 // Validation mirrors the reference's panics: assert!(k<=31) (src/nthash_avx512_32.rs:33) for the SIMD modes,
@@ -270,7 +270,7 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         rc[b] = P.w31 ? (uint32_t)(SEED64[3 - b] >> 33) : (uint32_t)SEED64[3 - b];
     }
     h[5] = rc[5] = 1;
-    static const uint8_t code_of[6] = {0, 8, 16, 24, 128, 136};   // see s2k_kernels.cuh (table layout)
+    static const uint8_t code_of[6] = {0, 8, 16, 24, 32, 40};     // see s2k_kernels.cuh (table layout)
     if (P.simd) {                                    // low nibble, src/nthash_avx512_32.rs:178-193
         static const uint8_t nib[16] = {4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4};
         for (int i = 0; i < 256; ++i) P.lut[i] = code_of[nib[i & 15]];
@@ -280,11 +280,18 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         P.lut['N'] = code_of[4];
     }
     std::memset(P.xy, 0, sizeof(P.xy));
+    std::memset(P.xf, 0, sizeof(P.xf));
+    std::memset(P.x2, 0, sizeof(P.x2));
     for (int o = 0; o < 6; ++o)
         for (int i = 0; i < 6; ++i) {
-            const int slot = (4 * code_of[o] + code_of[i]) / 8;
-            P.xy[slot].x = rolw(h[o], P.l, w) ^ h[i];
-            P.xy[slot].y = rorw(rc[o], 1, w) ^ rolw(rc[i], P.l - 1, w);
+            const uint2 e = make_uint2(rolw(h[o], P.l, w) ^ h[i], rorw(rc[o], 1, w) ^ rolw(rc[i], P.l - 1, w));
+            P.xy[(8 * code_of[o] + code_of[i]) / 8] = e;
+            if (o < 4 && i < 4) {
+                P.xf[(4 * code_of[o] + code_of[i]) / 8] = e;
+                // two warm-up steps at once: nothing leaves, bases o then i enter
+                P.x2[(4 * code_of[o] + code_of[i]) / 8] =
+                    make_uint2(rolw(h[o], 1, w) ^ h[i], rorw(rolw(rc[o], P.l - 1, w), 1, w) ^ rolw(rc[i], P.l - 1, w));
+            }
         }
     return S2K_OK;
 }
@@ -394,6 +401,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.tile = tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
         std::memcpy(A.cls_lut, P.lut, 256);
         std::memcpy(A.xy, P.xy, sizeof(P.xy));
+        std::memcpy(A.xf, P.xf, sizeof(P.xf));
+        std::memcpy(A.x2, P.x2, sizeof(P.x2));
         CU(cudaMemsetAsync(small, 0, 64, st));
         S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, n_bases, tile_eff, n_tiles,
                    ptr<uint32_t>(ctx->d_tile_lb));

@@ -30,7 +30,7 @@
 #define S2K_SHARED static
 #else
 #include <cuda_runtime.h>
-#define S2K_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#define S2K_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
 #define S2K_SHARED __shared__
 #endif
 
@@ -61,11 +61,18 @@ constexpr int XB    = 256;          // capacity of the left context, in kept (HP
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
 constexpr int HL    = 1024;         // hit-list entries emitted per round
 constexpr int DIRTY_MAX = 62;
-// Base classes are stored pre-scaled so that one IMAD forms the table address: code(A,C,G,T) = 0,8,16,24 and
-// the two rare classes (seed 0 / seed 1) = 128,136.  Entry (out,in) lives at byte 4*code(out)+code(in): the sixteen
-// ACGT x ACGT entries fill bytes 0..127 exactly -- one bank each -- so table loads never conflict on ACGT input.
-constexpr int XYN   = 86;           // (4*136 + 136 + 8) / 8 table slots
-constexpr int ZC8   = 128;          // code of the class whose forward and reverse seeds are both 0
+// Base classes are stored pre-scaled by 8 (the size of a table entry): code(A,C,G,T) = 0,8,16,24 and the two rare
+// classes (seed 0 / seed 1) = 32,40.  Three tables of (forward, reverse) 32-bit pairs:
+//   xy  general: entry (out,in) at byte 8*code(out)+code(in) -- collision-free for all 6x6 combinations
+//   xf  ACGT only: entry (out,in) at byte 4*code(out)+code(in): the sixteen entries fill bytes 0..127 exactly, one
+//       bank each, so loads never conflict; four such offsets are formed at once as the bytes of W_out*4+W_in
+//   x2  ACGT only, warm-up: entry (c1,c2) at byte 4*code(c1)+code(c2) advances the hash state by two bases
+// With a rare class in play 4*out+in still is a multiple of 8 below 208 (an aligned load of a meaningless entry);
+// the thread notices (bit 5 of some code it touched) and redoes its owners through xy.
+constexpr int XYN   = 46;           // (8*40 + 40) / 8 + 1 table slots
+constexpr int XFN   = 32;           // 26 reachable slots, rounded up
+constexpr int ZC8   = 32;           // code of the class whose forward and reverse seeds are both 0
+constexpr uint32_t RARE4 = 0x20202020u;   // bit 5 of every byte: set only in the codes of the two rare classes
 
 constexpr uint64_t FLAG_AGG  = 1ull << 62;
 constexpr uint64_t FLAG_INCL = 2ull << 62;
@@ -91,7 +98,9 @@ struct K1Args {
     uint32_t  n_tiles, tile, halo;
     uint32_t  l, d, need, thr;
     uint8_t   cls_lut[256];      // raw byte -> 8 * base class (classes 0..5)
-    uint2     xy[XYN];           // byte offset 4*code(out)+code(in) -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
+    uint2     xy[XYN];           // byte offset 8*code(out)+code(in) -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
+    uint2     xf[XFN];           // the same for ACGT x ACGT at byte offset 4*code(out)+code(in)
+    uint2     x2[XFN];           // (c1,c2) at 4*code(c1)+code(c2) -> (rol(h[c1],1)^h[c2], ror(r[c1],1)^r[c2]), r[c]=rol(rc[c],l-1)
 };
 
 struct Smem {
@@ -108,6 +117,8 @@ struct Smem {
     uint16_t qmap[(XB + WIN) / 64 + 2];      // chunk holding kept base 64*m (coarse inverse of qoff)
     uint2    xy[XYN];
     uint16_t hl[HL];
+    alignas(128) uint2 xf[XFN];              // 128-byte aligned: the 16 live entries cover the 32 banks once
+    alignas(128) uint2 x2[XFN];
     uint8_t  lut[256];
     uint32_t wsum[8];
     uint32_t tile_id, hk;
@@ -190,6 +201,16 @@ template <bool W31> __device__ __forceinline__ uint32_t ror1(uint32_t x)
     if (W31) return (x >> 1) | ((x & 1u) << 30);
     return __funnelshift_r(x, x, 1);
 }
+template <bool W31> __device__ __forceinline__ uint32_t rol2(uint32_t x)
+{
+    if (W31) return ((x << 2) | (x >> 29)) & 0x7fffffffu;
+    return __funnelshift_l(x, x, 2);
+}
+template <bool W31> __device__ __forceinline__ uint32_t ror2(uint32_t x)
+{
+    if (W31) return (x >> 2) | ((x & 3u) << 29);
+    return __funnelshift_r(x, x, 2);
+}
 // Sequence-start flags are sparse: remember which bitmap words were touched so that the next tile clears those
 // instead of zeroing four bitmaps.  More than DIRTY_MAX touched words -> the next tile zeroes everything.
 __device__ __forceinline__ void flag_raw(Smem &S, int par, uint32_t x, bool is_short)
@@ -208,7 +229,7 @@ __device__ __forceinline__ void flag_owner(Smem &S, int par, int oo, bool is_sho
 }
 __device__ __forceinline__ uint2 xy_at(const Smem &S, uint32_t out8, uint32_t in8)
 {
-    return *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(S.xy) + (out8 << 2) + in8);
+    return *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(S.xy) + (out8 << 3) + in8);
 }
 
 // Chunk (32 raw bases) that holds the kept base with window index q >= 0.
@@ -222,6 +243,100 @@ __device__ __forceinline__ int chunk_of(const Smem &S, int q)
 __device__ __forceinline__ int64_t pos_in_chunk(const Smem &S, int64_t W0, int c, int q)
 {
     return W0 + 32 * c + nth_set_bit(S.keepw[c], q - (int)S.qoff[c]);
+}
+
+// ------------------------------------------------------------------------------------------------ hash stage
+// One thread, CH consecutive owners.  cb[i] = class code of the last base of owner i's l-mer (cb is 4-aligned);
+// cb[i-l] = the base leaving the window.  Selected owners: bit i of mask, hash to hs[i].
+//
+// hash_owners_bytes: any classes.  Per owner two byte loads, one IMAD (8*out+in), one 8-byte load from xy.
+template <bool W31>
+__device__ __forceinline__ void hash_owners_bytes(const Smem &S, const uint8_t *cb, int l, uint32_t thr, uint32_t *hs,
+                                                  unsigned long long (&mask)[MW])
+{
+    uint32_t fh = 0, rh = 0;
+    for (int j = 1 - l; j < 0; ++j) {                  // warm-up: first l-1 bases of owner 0's l-mer
+        const uint2 tt = xy_at(S, ZC8, cb[j]);
+        fh = rol1<W31>(fh) ^ tt.x;
+        rh = ror1<W31>(rh) ^ tt.y;
+    }
+    const uint8_t *co = cb - l;
+#pragma unroll 4
+    for (int i = 0; i < CH; ++i) {
+        const uint2 tt = xy_at(S, i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8, cb[i]);
+        fh = rol1<W31>(fh) ^ tt.x;
+        rh = ror1<W31>(rh) ^ tt.y;
+        const uint32_t hv = min(fh, rh);
+        if (hv <= thr) { mask[i >> 6] |= 1ull << (i & 63); hs[i] = hv; }
+    }
+}
+// hash_owners_words: the common case, every class among A,C,G,T.  Class bytes are read as words; the four table
+// offsets of a group of owners are the bytes of W_out*4 + W_in (one IMAD), split with PRMT; the warm-up advances two
+// bases per table load.  Returns the OR of every code word it looked at: a bit of RARE4 set means the result is
+// meaningless (loads stayed aligned and inside the tables) and the caller falls back to hash_owners_bytes.
+template <bool W31>
+__device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, const uint8_t *cb, int l, uint32_t thr, uint32_t *hs,
+                                                      unsigned long long (&mask)[MW])
+{
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cb);
+    const uint8_t *xf = reinterpret_cast<const uint8_t *>(S.xf), *x2 = reinterpret_cast<const uint8_t *>(S.x2);
+    uint32_t fh = 0, rh = 0, seen = 0;
+    {   // warm-up over cb[1-l .. -1]: an odd first base alone (general table), then pairs
+        int j = 1 - l;
+        if ((l - 1) & 1) {
+            const uint32_t c = cb[j];
+            const uint2 tt = xy_at(S, ZC8, c);
+            fh = tt.x; rh = tt.y; seen |= c;
+            ++j;
+        }
+        const int np = (l - 1) >> 1;                       // pairs
+        const int jw = j >> 2;                             // word holding cb[j] (floor: j < 0)
+        const uint32_t sh = (uint32_t)(j & 3) * 8u;
+        uint32_t lo = cw[jw];
+        for (int p = 0; p < np; p += 2) {
+            const uint32_t hi = cw[jw + 1 + (p >> 1)];
+            const uint32_t w = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            seen |= w;
+            const uint32_t pi = w * 4u + (w >> 8);         // byte 0: 4*c0+c1, byte 2: 4*c2+c3
+            uint2 tt = *reinterpret_cast<const uint2 *>(x2 + (pi & 0xffu));
+            fh = rol2<W31>(fh) ^ tt.x;
+            rh = ror2<W31>(rh) ^ tt.y;
+            if (p + 1 < np) {
+                tt = *reinterpret_cast<const uint2 *>(x2 + __byte_perm(pi, 0u, 0x4442u));
+                fh = rol2<W31>(fh) ^ tt.x;
+                rh = ror2<W31>(rh) ^ tt.y;
+            }
+        }
+    }
+    const int oq = -((l + 3) >> 2);                        // word of cb[-l] relative to cw, and its byte shift
+    const uint32_t ob = (uint32_t)((-l) & 3) * 8u;
+    const uint32_t *ow = cw + oq;
+    uint32_t o_prev = ow[0];
+#pragma unroll
+    for (int g = 0; g < CH / 4; ++g) {
+        const uint32_t w_in = cw[g], o_next = ow[g + 1];
+        const uint32_t w_out = __funnelshift_r(o_prev, o_next, ob);
+        o_prev = o_next;
+        seen |= w_in | w_out;
+        const uint32_t i4 = w_out * 4u + w_in;
+        uint32_t hv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint2 tt;
+            if (g == 0 && k == 0) tt = xy_at(S, ZC8, w_in & 0xffu);     // owner 0: nothing leaves yet
+            else tt = *reinterpret_cast<const uint2 *>(xf + __byte_perm(i4, 0u, 0x4440u + k));
+            fh = rol1<W31>(fh) ^ tt.x;
+            rh = ror1<W31>(rh) ^ tt.y;
+            hv[k] = min(fh, rh);
+        }
+        if (min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= thr) {         // rare: ~8 % of groups at d=0.01
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (hv[k] <= thr) { mask[(4 * g + k) >> 6] |= 1ull << ((4 * g + k) & 63); hs[4 * g + k] = hv[k]; }
+        }
+    }
+    return seen;
 }
 
 // ------------------------------------------------------------------------------------------------ tile bounds
@@ -268,6 +383,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 
     for (int i = tid; i < 256; i += NT) S.lut[i] = A.cls_lut[i];
     if (tid < XYN) S.xy[tid] = A.xy[tid];
+    if (tid < XFN) { S.xf[tid] = A.xf[tid]; S.x2[tid] = A.x2[tid]; }
     for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
     for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
     for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
@@ -404,7 +520,11 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             }
         }
         __syncthreads();
-        const uint32_t hk = S.hk;
+        // Owner space starts up to 3 kept bases inside the halo (those pseudo-owners are masked out below) so that
+        // every thread's class bytes begin on a word boundary of S.code: the hash stage reads them as words.
+        const uint32_t hk_real = S.hk;
+        const int dlt = (int)((hk_real - (uint32_t)d) & 3u);
+        const int hk = (int)hk_real - dlt;
         {   // sequence starts among this thread's kept bases -> owner-space flags (rare)
             const unsigned long long keep = ((unsigned long long)khi << 32) | klo;
             unsigned long long sw = (((unsigned long long)S.startw[2 * tid + 1] << 32) | S.startw[2 * tid]) & keep;
@@ -412,14 +532,14 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             while (sw) {
                 const int b = __ffsll((long long)sw) - 1;
                 sw &= sw - 1;
-                const int oo = (int)q + __popcll(keep & lowmask64(b)) - (int)hk + XB;
+                const int oo = (int)q + __popcll(keep & lowmask64(b)) - hk + XB;
                 if (oo >= 0) flag_owner(S, par, oo, (sh2 >> b) & 1ull);
             }
         }
         // ---- S4b: not enough context in the halo -> walk back through the sequence (rare: long homopolymers)
-        const bool need_walk = HPC && (int64_t)S.s0 < W0 && hk < A.need;
+        const bool need_walk = HPC && (int64_t)S.s0 < W0 && hk_real < A.need;
         if (need_walk && warp == 0) {
-            uint32_t remaining = A.need - hk, taken = 0;
+            uint32_t remaining = A.need - hk_real, taken = 0;
             const int64_t s0 = (int64_t)S.s0;
             int64_t hi = W0;
             while (remaining > 0 && hi > s0) {
@@ -436,7 +556,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                     const uint32_t slot = taken + rank;            // 0 = nearest to the window
                     S.code[XB - 1 - (int)slot] = S.lut[b];
                     S.ctxpos[slot] = (uint32_t)(W0 - g);
-                    if (g == s0) { const int oo = XB - 1 - (int)slot - (int)hk; if (oo >= 0) flag_owner(S, par, oo, false); }
+                    if (g == s0) { const int oo = XB - 1 - (int)slot - hk; if (oo >= 0) flag_owner(S, par, oo, false); }
                 }
                 const uint32_t c = min((uint32_t)__popc(m), remaining);
                 taken += c; remaining -= c; hi = lo;
@@ -445,7 +565,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         __syncthreads();
 
         // ---- S5 + S6a: rolling canonical ntHash over the owners, CAP per pass; block scan of hit counts
-        const uint32_t n_own = wk - hk;                   // kept bases in [T0, T1): each completes one l-mer
+        const uint32_t n_own = wk - (uint32_t)hk;         // kept bases in [T0, T1) (+dlt): each completes one l-mer
         uint32_t tile_min = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
@@ -492,32 +612,13 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                         }
                     }
                 }
-                const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer
-                uint32_t fh = 0, rh = 0;
-                for (int j = 1 - l; j < 0; ++j) {                  // warm-up: first l-1 bases of owner 0's l-mer
-                    const uint2 tt = xy_at(S, ZC8, cb[j]);
-                    fh = rol1<W31>(fh) ^ tt.x;
-                    rh = ror1<W31>(rh) ^ tt.y;
-                }
-                const uint8_t *co = cb - l;
+                if (v0 == 0) invalid[0] |= lowmask64((uint32_t)dlt);   // the pseudo-owners inside the halo
+                const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer; 4-aligned
+                const uint32_t rare = hash_owners_words<W31>(S, cb, l, A.thr, hs + v0, mask);
+                if (rare & RARE4) {                                // a rare class among the bytes touched: redo via xy
 #pragma unroll
-                for (int i0 = 0; i0 < CH; i0 += 4) {
-                    uint32_t hv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = i0 + k;
-                        const uint32_t in8 = cb[i];
-                        const uint32_t out8 = i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8;
-                        const uint2 tt = xy_at(S, out8, in8);
-                        fh = rol1<W31>(fh) ^ tt.x;
-                        rh = ror1<W31>(rh) ^ tt.y;
-                        hv[k] = min(fh, rh);
-                    }
-                    if (min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= A.thr) {   // rare: ~8 % of groups at d=0.01
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (hv[k] <= A.thr) { mask[(i0 + k) >> 6] |= 1ull << ((i0 + k) & 63); hs[v0 + i0 + k] = hv[k]; }
-                    }
+                    for (int x = 0; x < MW; ++x) mask[x] = 0ull;
+                    hash_owners_bytes<W31>(S, cb, l, A.thr, hs + v0, mask);
                 }
 #pragma unroll
                 for (int x = 0; x < MW; ++x)                       // owners >= n_u hashed garbage
@@ -543,7 +644,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         if (tid == 0) {
             const unsigned long long r0 = tile_min ? atomicAdd(A.cursor, (unsigned long long)tile_min) : 0ull;
             S.rec0 = r0;
-            A.tile_info[t] = make_uint4(tile_min, n_own, (uint32_t)r0, (uint32_t)(r0 >> 32));
+            A.tile_info[t] = make_uint4(tile_min, wk - hk_real, (uint32_t)r0, (uint32_t)(r0 >> 32));
             if (r0 + tile_min > A.min_cap) atomicOr(A.err, ERR_CAP);
         }
         __syncthreads();
@@ -570,7 +671,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             const uint32_t n_round = min((uint32_t)HL, tile_min - base);
             for (uint32_t j = tid; j < n_round; j += NT) {
                 const int v = S.hl[j];
-                const int qo = (int)hk + v;                // window index of the owner base
+                const int qo = hk + v;                     // window index of the owner base
                 const uint32_t h = hs[v];
                 int c = chunk_of(S, qo);
                 const int64_t g_own = pos_in_chunk(S, W0, c, qo);
@@ -596,7 +697,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             const uint64_t so = A.seq_off[i];
             const uint32_t x = (uint32_t)((int64_t)so - W0);
             const uint32_t qx = S.qoff[x >> 5] + __popc(S.keepw[x >> 5] & lowmask(x & 31));
-            const uint32_t v = qx - hk;
+            const uint32_t v = qx - (uint32_t)hk;
             const uint32_t pass = v >= (uint32_t)CAP ? 1u : 0u;
             const uint32_t vv = v - pass * CAP, u = vv / CH, bit = vv - u * CH;
             uint32_t hb = S.hitpre[pass][u];
@@ -604,7 +705,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             for (int x = 0; x < MW; ++x)
                 hb += __popcll(S.hitw[pass][u][x] & lowmask64((uint32_t)max(min((int)bit - 64 * x, 64), 0)));
             A.min_off[i] = hb;
-            if (A.hpc_off) A.hpc_off[i] = v;
+            if (A.hpc_off) A.hpc_off[i] = qx - hk_real;
         }
     }
 }
