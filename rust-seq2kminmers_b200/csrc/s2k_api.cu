@@ -231,6 +231,7 @@ struct Plan {
     bool hpc, simd, w31, quirk;
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
+    bool dense;      // >= ~0.5 % of the owners selected: bookkeeping per owner instead of a test per group of four
     uint8_t lut[256];   // raw byte -> code of its base class
     uint2 xy[XYN], xf[XFN], x2[XFN];
 };
@@ -262,6 +263,7 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     else excl = (uint64_t)bs + 1;
     P.none = excl == 0;
     P.thr = P.none ? 0u : (uint32_t)(excl - 1);
+    P.dense = (double)excl / (P.w31 ? 2147483648.0 : 4294967296.0) >= 0.0027;   // the canonical minimum doubles the rate
     // base classes: 0..3 = A C G T, 4 = seed 0, 5 = seed 1
     const int w = P.w31 ? 31 : 32;
     uint32_t h[8] = {0}, rc[8] = {0};
@@ -298,15 +300,21 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
 
 template <typename T> T *ptr(Buf &b) { return reinterpret_cast<T *>(b.p); }
 
+typedef void (*MinimizerKernel)(const K1Args);
+MinimizerKernel minimizer_kernel(bool hpc, bool w31, bool dense)
+{
+    static const MinimizerKernel k[8] = {
+        k_minimizers<false, false, false>, k_minimizers<true, false, false>, k_minimizers<false, true, false>, k_minimizers<true, true, false>,
+        k_minimizers<false, false, true>,  k_minimizers<true, false, true>,  k_minimizers<false, true, true>,  k_minimizers<true, true, true>};
+    return k[(hpc ? 1 : 0) | (w31 ? 2 : 0) | (dense ? 4 : 0)];
+}
+
 
 int set_attrs(s2k_ctx *ctx)
 {
     if (ctx->attr_set) return S2K_OK;
     const int smem = (int)sizeof(Smem);
-    CU(cudaFuncSetAttribute(k_minimizers<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(k_minimizers<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(k_minimizers<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(k_minimizers<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int v = 0; v < 8; ++v) CU(cudaFuncSetAttribute(minimizer_kernel(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ctx->attr_set = true;
     return S2K_OK;
 }
@@ -379,8 +387,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         n_tiles = (uint32_t)n_tiles64;
         const int max_grid = ctx->sm_count * S2K_MINB;
         const size_t hscr_words = (size_t)max_grid * WIN, smem = sizeof(Smem);
-        void (*kfn)(const K1Args) = P.hpc ? (P.w31 ? k_minimizers<true, true> : k_minimizers<true, false>)
-                                          : (P.w31 ? k_minimizers<false, true> : k_minimizers<false, false>);
+        void (*kfn)(const K1Args) = minimizer_kernel(P.hpc, P.w31, P.dense);
         if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;

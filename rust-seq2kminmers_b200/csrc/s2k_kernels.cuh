@@ -274,7 +274,10 @@ __device__ __forceinline__ void hash_owners_bytes(const Smem &S, const uint8_t *
 // offsets of a group of owners are the bytes of W_out*4 + W_in (one IMAD), split with PRMT; the warm-up advances two
 // bases per table load.  Returns the OR of every code word it looked at: a bit of RARE4 set means the result is
 // meaningless (loads stayed aligned and inside the tables) and the caller falls back to hash_owners_bytes.
-template <bool W31>
+// DENSE: at the usual densities some lane of the warp selects an owner in almost every group of four (2 % of the
+// owners at d = 0.01: 1 - 0.98^128 = 92 %), so a "rare" branch around the bookkeeping would nearly always run; the
+// three predicated instructions per owner are cheaper.  Sparse selections keep the test per group.
+template <bool W31, bool DENSE>
 __device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, const uint8_t *cb, int l, uint32_t thr, uint32_t *hs,
                                                       unsigned long long (&mask)[MW])
 {
@@ -330,7 +333,7 @@ __device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, const uint8
             rh = ror1<W31>(rh) ^ tt.y;
             hv[k] = min(fh, rh);
         }
-        if (min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= thr) {         // rare: ~8 % of groups at d=0.01
+        if (DENSE || min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= thr) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (hv[k] <= thr) { mask[(4 * g + k) >> 6] |= 1ull << ((4 * g + k) & 63); hs[4 * g + k] = hv[k]; }
@@ -372,7 +375,7 @@ __global__ void k_tile_bounds(const uint64_t *__restrict__ seq_off, uint64_t n_s
 #ifndef S2K_MINB
 #define S2K_MINB 4                  // CTAs per SM the minimizer kernel is compiled for (register cap)
 #endif
-template <bool HPC, bool W31>
+template <bool HPC, bool W31, bool DENSE>
 __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_constant__ K1Args A)
 {
     S2K_DYN_SMEM(smem_raw);
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 }
                 if (v0 == 0) invalid[0] |= lowmask64((uint32_t)dlt);   // the pseudo-owners inside the halo
                 const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer; 4-aligned
-                const uint32_t rare = hash_owners_words<W31>(S, cb, l, A.thr, hs + v0, mask);
+                const uint32_t rare = hash_owners_words<W31, DENSE>(S, cb, l, A.thr, hs + v0, mask);
                 if (rare & RARE4) {                                // a rare class among the bytes touched: redo via xy
 #pragma unroll
                     for (int x = 0; x < MW; ++x) mask[x] = 0ull;
