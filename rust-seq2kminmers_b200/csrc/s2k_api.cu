@@ -629,6 +629,16 @@ int s2k_last_kernel_ms(const s2k_ctx *ctx, double *minimizer_ms, double *window_
 }
 
 uint64_t s2k_launch_count(const s2k_ctx *ctx) { return ctx ? ctx->launches : 0; }
+#if defined(S2K_PHASE_CLOCKS) && !defined(S2K_EMU)
+// debug builds only (tools/phase_clocks.py): cycles thread 0 of every CTA spent per phase of k_minimizers since the last call
+extern "C" int s2k_debug_phase_clocks(unsigned long long *out16)
+{
+    if (cudaMemcpyFromSymbol(out16, s2k::g_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(s2k::g_phase, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int s2k_last_kernel_kind(const s2k_ctx *ctx) { return ctx ? ctx->kernel_kind : -1; }
 
 int s2k_host_alloc(size_t bytes, void **out)

@@ -61,6 +61,7 @@ constexpr int XB    = 256;          // capacity of the left context, in kept (HP
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
 constexpr int HL    = 1024;         // hit-list entries emitted per round
 constexpr int DIRTY_MAX = 62;
+constexpr int SOC   = 128;          // sequence offsets cached per tile (tiles with more starts search global memory)
 // Base classes are stored pre-scaled by 8 (the size of a table entry): code(A,C,G,T) = 0,8,16,24 and the two rare
 // classes (seed 0 / seed 1) = 32,40.  Three tables of (forward, reverse) 32-bit pairs:
 //   xy  general: entry (out,in) at byte 8*code(out)+code(in) -- collision-free for all 6x6 combinations
@@ -121,7 +122,10 @@ struct Smem {
     alignas(128) uint2 x2[XFN];
     uint8_t  lut[256];
     uint32_t wsum[8];
-    uint32_t tile_id, hk;
+    uint32_t hk;
+    uint32_t next[2];                        // tile ticket by parity: the next one is drawn while this one is processed
+    uint32_t nlb[2][2];                      // ... with its tile_lb pair
+    unsigned long long soc[SOC + 1];         // seq_off[lb-1 .. lb-1+SOC]: the emission looks sequences up here
     uint32_t n_dirty[2];                     // flag words set during this tile (cleared at the next loop top);
     uint16_t dirty[2][DIRTY_MAX];            // double-buffered by tile parity.  bit 15: f1/f2, else startw/shortw
     unsigned long long s0, rec0;
@@ -375,6 +379,17 @@ __global__ void k_tile_bounds(const uint64_t *__restrict__ seq_off, uint64_t n_s
 #ifndef S2K_MINB
 #define S2K_MINB 4                  // CTAs per SM the minimizer kernel is compiled for (register cap)
 #endif
+// -DS2K_PHASE_CLOCKS (tools/phase_clocks.py): thread 0 of every CTA sums the cycles between phase marks into g_phase.
+#if defined(S2K_PHASE_CLOCKS) && !defined(S2K_EMU)
+__device__ unsigned long long g_phase[16];
+#define PHASE_DECL long long ph_t = clock64(); unsigned long long ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PHASE(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); ph_acc[i] += (unsigned long long)(n_ - ph_t); ph_t = n_; } } while (0)
+#define PHASE_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 10; ++i_) atomicAdd(&g_phase[i_], ph_acc[i_]); } while (0)
+#else
+#define PHASE_DECL
+#define PHASE(i)
+#define PHASE_FLUSH
+#endif
 template <bool HPC, bool W31, bool DENSE>
 __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_constant__ K1Args A)
 {
@@ -391,34 +406,33 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
     for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
     if (tid == 0) { S.n_dirty[0] = 0; S.n_dirty[1] = 0; }
-    int par = 1;                                           // parity of the tile being processed
+    if (tid == 0) {                                        // first ticket; later ones are drawn a tile ahead
+        const uint32_t t0 = atomicAdd(A.ticket, 1u);
+        S.next[0] = t0;
+        if (t0 < A.n_tiles) {
+            S.nlb[0][0] = A.tile_lb[t0];
+            S.nlb[0][1] = t0 + 1 == A.n_tiles ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t0 + 1];
+        }
+    }
+    int par = 0;                                           // parity of the tile being processed
+    PHASE_DECL;
 
     for (;;) {
-        __syncthreads();                                   // everyone is done with the previous tile
-        if (tid == 0) S.tile_id = atomicAdd(A.ticket, 1u);
-        {   // clear the flag words the previous tile (parity `par`) touched
-            const uint32_t nd = S.n_dirty[par];
-            if (nd > DIRTY_MAX) {
-                for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
-                for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
-            } else if ((uint32_t)tid < nd) {
-                const uint32_t e = S.dirty[par][tid];
-                if (e & 0x8000u) { S.f1[e & 0x7fffu] = 0; S.f2[e & 0x7fffu] = 0; }
-                else { S.startw[e] = 0; S.shortw[e] = 0; }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) S.n_dirty[par] = 0;                  // consumed; reused by the tile after this one
-        par ^= 1;
-        const uint32_t t = S.tile_id;
+        __syncthreads();                                   // the previous tile is done and has wiped its flag words
+        const uint32_t t = S.next[par];
         if (t >= A.n_tiles) break;
+        uint32_t t_next = 0;
+        if (tid == 0) {
+            S.n_dirty[par ^ 1] = 0;                        // the previous tile's list has been consumed
+            t_next = atomicAdd(A.ticket, 1u);              // in flight while this tile is staged; parked in S.next below
+        }
+        PHASE(0);
 
         const int64_t T0 = (int64_t)((uint64_t)t * A.tile);
         const int64_t T1 = min(T0 + (int64_t)A.tile, (int64_t)A.n_bases);
         const int64_t W0 = T0 - (int64_t)A.halo;
         const bool last_tile = (uint64_t)T1 == A.n_bases;
-        const uint32_t lb = A.tile_lb[t];
-        const uint32_t ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
+        const uint32_t lb = S.nlb[par][0], ub = S.nlb[par][1];
 
         // ---- S3a: this thread's 64 raw bases, global -> registers (issued first: the latency overlaps S2)
         const int64_t g0 = W0 + RAWPT * tid;
@@ -445,6 +459,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // ---- S2: sequence starts inside the tile (and the start of the sequence containing T0, if in the window)
         for (uint32_t i = lb + tid; i < ub; i += NT) {
             const uint64_t so = A.seq_off[i];
+            if (i - lb < (uint32_t)SOC) S.soc[i - lb + 1] = so;
             if (so < (uint64_t)T1) {
                 const uint64_t len = A.seq_off[i + 1] - so;
                 flag_raw(S, par, (uint32_t)((int64_t)so - W0), len > 0 && len <= (uint64_t)l);
@@ -452,9 +467,11 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         }
         if (tid == 0) {
             const uint64_t so_lb = A.seq_off[lb];
+            const uint64_t so_pr = lb ? A.seq_off[lb - 1] : 0ull;
+            S.soc[0] = so_pr;
             unsigned long long s0 = (unsigned long long)T0;
             if (so_lb != (uint64_t)T0) {                   // the sequence containing T0 started earlier
-                s0 = A.seq_off[lb - 1];
+                s0 = so_pr;
                 if ((int64_t)s0 >= W0) {
                     flag_raw(S, par, (uint32_t)((int64_t)s0 - W0), so_lb - s0 <= (uint64_t)l);
                 }
@@ -462,6 +479,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             S.s0 = s0;
         }
         __syncthreads();
+        PHASE(1);
 
         // ---- S3b: keep mask, block scan of kept counts
         uint32_t klo, khi;
@@ -498,6 +516,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         for (uint32_t m = (q + 63u) & ~63u; m < q + clo + __popc(khi); m += 64)
             S.qmap[m >> 6] = (uint16_t)(m < q + clo ? 2 * tid : 2 * tid + 1);
 
+        PHASE(2);
         // ---- S4: compaction (predicated byte stores in HPC order)
         if (!HPC && (klo & khi) == 0xffffffffu && ((XB + q) & 15u) == 0) {
             // every base kept (no HPC): byte stores would advance at a 64-byte lane stride = 16-way bank conflicts.
@@ -522,7 +541,9 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 if (kb) { *cp = S.lut[__byte_perm(w[b >> 2], 0u, 0x4440u + (b & 3))]; ++cp; }
             }
         }
+        if (tid == 0) S.next[par ^ 1] = t_next;           // the ticket drawn at the top has long arrived
         __syncthreads();
+        PHASE(3);
         // Owner space starts up to 3 kept bases inside the halo (those pseudo-owners are masked out below) so that
         // every thread's class bytes begin on a word boundary of S.code: the hash stage reads them as words.
         const uint32_t hk_real = S.hk;
@@ -566,6 +587,14 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             }
         }
         __syncthreads();
+        PHASE(4);
+        const uint32_t tn = S.next[par ^ 1];
+#ifndef S2K_EMU
+        if (tn < A.n_tiles && tid < WIN / 128) {           // pull the next tile's bases into L2 while this one is hashed
+            const int64_t a = (int64_t)((uint64_t)tn * A.tile) - (int64_t)A.halo + 128 * tid;
+            if (a >= 0 && a < (int64_t)A.n_bases) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.bases + a));
+        }
+#endif
 
         // ---- S5 + S6a: rolling canonical ntHash over the owners, CAP per pass; block scan of hit counts
         const uint32_t n_own = wk - (uint32_t)hk;         // kept bases in [T0, T1) (+dlt): each completes one l-mer
@@ -643,15 +672,26 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             }
         }
 
-        // ---- S6b: claim a contiguous run of records for this tile (tiles land in any order; k_finalize sorts them out)
+        PHASE(5);
+        // ---- S6b: claim a contiguous run of records for this tile (tiles land in any order; k_finalize sorts them out).
+        // Thread 0 fires the atomic and the loads of the next tile's sequence bounds here and picks the results up
+        // after the barrier / at the end of the tile, so that nobody waits for their latency.
+        unsigned long long r0 = 0ull;
+        uint32_t nlb0 = 0, nlb1 = 0;
         if (tid == 0) {
-            const unsigned long long r0 = tile_min ? atomicAdd(A.cursor, (unsigned long long)tile_min) : 0ull;
-            S.rec0 = r0;
+            if (tile_min) r0 = atomicAdd(A.cursor, (unsigned long long)tile_min);
+            if (tn < A.n_tiles) {
+                nlb0 = A.tile_lb[tn];
+                nlb1 = tn + 1 == A.n_tiles ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[tn + 1];
+            }
+        }
+        __syncthreads();                                   // hit masks and prefixes of all threads are in place
+        if (tid == 0) {
+            S.rec0 = r0;                                   // read after the barrier inside the emission loop
             A.tile_info[t] = make_uint4(tile_min, wk - hk_real, (uint32_t)r0, (uint32_t)(r0 >> 32));
             if (r0 + tile_min > A.min_cap) atomicOr(A.err, ERR_CAP);
         }
-        __syncthreads();
-        const uint64_t rec0 = S.rec0;
+        PHASE(6);
 
         // ---- S7: ordered hit list in shared memory, then one thread per minimizer
         for (uint32_t base = 0; base < tile_min; base += HL) {
@@ -671,6 +711,8 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 }
             }
             __syncthreads();
+            const uint64_t rec0 = S.rec0;
+            const bool cached = ub - lb <= (uint32_t)SOC;
             const uint32_t n_round = min((uint32_t)HL, tile_min - base);
             for (uint32_t j = tid; j < n_round; j += NT) {
                 const int v = S.hl[j];
@@ -685,16 +727,18 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 uint32_t lo = lb, hi = ub;                 // first i in [lb,ub) with seq_off[i] > g_own
                 while (lo < hi) {
                     const uint32_t mid = lo + ((hi - lo) >> 1);
-                    if (A.seq_off[mid] <= (uint64_t)g_own) lo = mid + 1; else hi = mid;
+                    const uint64_t sm = cached ? S.soc[mid - lb + 1] : A.seq_off[mid];
+                    if (sm <= (uint64_t)g_own) lo = mid + 1; else hi = mid;
                 }
                 const uint32_t rid = lo - 1;
-                const uint64_t so = A.seq_off[rid];
+                const uint64_t so = cached ? S.soc[lo - lb] : A.seq_off[rid];
                 const uint64_t idx = rec0 + base + j;
                 if (idx < A.min_cap)
                     A.min_out[idx] = make_uint4(h, (uint32_t)((uint64_t)g_start - so),
                                                 (uint32_t)((uint64_t)g_own - (uint64_t)d - so), rid);
             }
         }
+        PHASE(7);
         // ---- S8: per-sequence offsets for every sequence starting in this tile
         for (uint32_t i = lb + tid; i < ub; i += NT) {
             const uint64_t so = A.seq_off[i];
@@ -710,7 +754,22 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             A.min_off[i] = hb;
             if (A.hpc_off) A.hpc_off[i] = qx - hk_real;
         }
+        {   // wipe the flag words this tile touched (their last readers passed a barrier in the hash stage)
+            const uint32_t nd = S.n_dirty[par];
+            if (nd > DIRTY_MAX) {
+                for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
+                for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
+            } else if ((uint32_t)tid < nd) {
+                const uint32_t e = S.dirty[par][tid];
+                if (e & 0x8000u) { S.f1[e & 0x7fffu] = 0; S.f2[e & 0x7fffu] = 0; }
+                else { S.startw[e] = 0; S.shortw[e] = 0; }
+            }
+        }
+        if (tid == 0) { S.nlb[par ^ 1][0] = nlb0; S.nlb[par ^ 1][1] = nlb1; }
+        par ^= 1;
+        PHASE(8);
     }
+    PHASE_FLUSH;
 }
 
 
