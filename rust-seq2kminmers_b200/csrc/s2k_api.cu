@@ -378,6 +378,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     }
 
     uint32_t n_tiles = 0, tile_eff = 0;
+    uint64_t tmp_records = 0;                          // records d_tmp holds in the layout of the last launch
+    bool regions = true;                               // per-CTA append regions first; one global allocator on the rerun
     ctx->kernel_kind = 0;
     for (int attempt = 0;; ++attempt) {
         if (attempt == 4) return fail(ctx, S2K_ERR_INTERNAL, "minimizer kernel did not converge");
@@ -391,7 +393,13 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;
-        if ((rc = ensure(ctx, ctx->d_tmp, cap * sizeof(uint4), false))) return rc;
+        // Per-CTA append regions get 1/8 + 1024 records of slack on top of an even share: tiles are handed out
+        // dynamically, so the CTAs' totals differ by a few tiles' worth.
+        const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
+        const uint64_t slack = (ctx->flags & S2K_DEBUG_TINY_CAP) ? 1 : cap / (8ull * (uint64_t)grid) + 1024;
+        const uint64_t region_cap = regions ? cap / (uint64_t)grid + slack : 0;
+        const uint64_t tmp_cap = regions ? region_cap * (uint64_t)grid : cap;
+        if ((rc = ensure(ctx, ctx->d_tmp, tmp_cap * sizeof(uint4), false))) return rc;
 
         K1Args A;
         A.bases = d_bases; A.seq_off = d_seq_off;
@@ -399,7 +407,9 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.ticket = reinterpret_cast<uint32_t *>(small + 4);
         A.cursor = reinterpret_cast<unsigned long long *>(small + 0);
         A.tile_info = ptr<uint4>(ctx->d_tile_info);
-        A.min_out = ptr<uint4>(ctx->d_tmp); A.min_cap = cap;
+        A.min_out = ptr<uint4>(ctx->d_tmp); A.min_cap = tmp_cap;
+        tmp_records = tmp_cap;
+        A.region_cap = region_cap;
         A.min_off = ptr<uint64_t>(ctx->d_min_off);
         A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
         A.hscr = ptr<uint32_t>(ctx->d_hscr);
@@ -413,7 +423,6 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         CU(cudaMemsetAsync(small, 0, 64, st));
         S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, n_bases, tile_eff, n_tiles,
                    ptr<uint32_t>(ctx->d_tile_lb));
-        const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
         Timing &T = ctx->tm;
         const bool rec = T.enabled && T.n < 64;
         if (rec) cudaEventRecord(T.ev[T.n][0], st);
@@ -425,8 +434,9 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         n_min = hsmall[0];
-        if (n_min <= cap) break;
-        cap = n_min;                                   // exact size known now: rerun once
+        if (regions ? !((uint32_t)hsmall[2] & ERR_CAP) : n_min <= cap) break;
+        cap = std::max(cap, n_min);                    // exact size known now: rerun once, with one global allocator
+        regions = false;
     }
     if ((rc = ensure(ctx, ctx->d_mins, std::max<uint64_t>(n_min, 1) * sizeof(uint4), false))) return rc;
     {
@@ -443,7 +453,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         F.tile_info = ptr<uint4>(ctx->d_tile_info); F.tile_loc = tile_loc; F.chunk_base = chunk_base;
         F.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
         F.min_off = ptr<uint64_t>(ctx->d_min_off); F.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
-        F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = cap; F.n_tiles = n_tiles; F.tile = tile_eff;
+        F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = tmp_records; F.n_tiles = n_tiles; F.tile = tile_eff;
         const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 8);
         S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
         CU(cudaGetLastError());

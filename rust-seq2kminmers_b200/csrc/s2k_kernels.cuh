@@ -91,6 +91,8 @@ struct K1Args {
     uint4    *tile_info;         // n_tiles: (hits, kept bases, first record lo, hi)
     uint4    *min_out;           // minimizer records (hash, start, end, seq), grouped by tile, tiles in any order
     uint64_t  min_cap;
+    uint64_t  region_cap;        // > 0: CTA b appends to records [b*region_cap, (b+1)*region_cap) without any atomic;
+                                 // 0: one global bump allocator (the rerun after a region overflowed)
     uint64_t *min_off;           // n_seqs + 1: minimizers of the tile before the sequence start (tile-local)
     uint64_t *hpc_off;           // n_seqs + 1 or null: kept bases of the tile before the sequence start
     uint32_t *hscr;              // gridDim.x * WIN words: per-CTA stash of selected hashes (stays in L2)
@@ -128,7 +130,7 @@ struct Smem {
     unsigned long long soc[SOC + 1];         // seq_off[lb-1 .. lb-1+SOC]: the emission looks sequences up here
     uint32_t n_dirty[2];                     // flag words set during this tile (cleared at the next loop top);
     uint16_t dirty[2][DIRTY_MAX];            // double-buffered by tile parity.  bit 15: f1/f2, else startw/shortw
-    unsigned long long s0, rec0;
+    unsigned long long s0, rec0, rec_lim, cur;   // cur: records this CTA has appended to its region
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
     if (tid == 0) { S.n_dirty[0] = 0; S.n_dirty[1] = 0; }
     if (tid == 0) {                                        // first ticket; later ones are drawn a tile ahead
+        S.cur = 0ull;
         const uint32_t t0 = atomicAdd(A.ticket, 1u);
         S.next[0] = t0;
         if (t0 < A.n_tiles) {
@@ -676,10 +679,15 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // ---- S6b: claim a contiguous run of records for this tile (tiles land in any order; k_finalize sorts them out).
         // Thread 0 fires the atomic and the loads of the next tile's sequence bounds here and picks the results up
         // after the barrier / at the end of the tile, so that nobody waits for their latency.
-        unsigned long long r0 = 0ull;
+        unsigned long long r0 = 0ull, lim = A.min_cap;
         uint32_t nlb0 = 0, nlb1 = 0;
         if (tid == 0) {
-            if (tile_min) r0 = atomicAdd(A.cursor, (unsigned long long)tile_min);
+            if (A.region_cap) {
+                const unsigned long long c = S.cur;
+                r0 = (unsigned long long)blockIdx.x * A.region_cap + c;
+                lim = ((unsigned long long)blockIdx.x + 1ull) * A.region_cap;
+                S.cur = c + tile_min;
+            } else if (tile_min) r0 = atomicAdd(A.cursor, (unsigned long long)tile_min);
             if (tn < A.n_tiles) {
                 nlb0 = A.tile_lb[tn];
                 nlb1 = tn + 1 == A.n_tiles ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[tn + 1];
@@ -687,9 +695,9 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         }
         __syncthreads();                                   // hit masks and prefixes of all threads are in place
         if (tid == 0) {
-            S.rec0 = r0;                                   // read after the barrier inside the emission loop
+            S.rec0 = r0; S.rec_lim = lim;                  // read after the barrier inside the emission loop
             A.tile_info[t] = make_uint4(tile_min, wk - hk_real, (uint32_t)r0, (uint32_t)(r0 >> 32));
-            if (r0 + tile_min > A.min_cap) atomicOr(A.err, ERR_CAP);
+            if (r0 + tile_min > lim) atomicOr(A.err, ERR_CAP);
         }
         PHASE(6);
 
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 }
             }
             __syncthreads();
-            const uint64_t rec0 = S.rec0;
+            const uint64_t rec0 = S.rec0, rec_lim = S.rec_lim;
             const bool cached = ub - lb <= (uint32_t)SOC;
             const uint32_t n_round = min((uint32_t)HL, tile_min - base);
             for (uint32_t j = tid; j < n_round; j += NT) {
@@ -733,7 +741,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 const uint32_t rid = lo - 1;
                 const uint64_t so = cached ? S.soc[lo - lb] : A.seq_off[rid];
                 const uint64_t idx = rec0 + base + j;
-                if (idx < A.min_cap)
+                if (idx < rec_lim)
                     A.min_out[idx] = make_uint4(h, (uint32_t)((uint64_t)g_start - so),
                                                 (uint32_t)((uint64_t)g_own - (uint64_t)d - so), rid);
             }
@@ -741,7 +749,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         PHASE(7);
         // ---- S8: per-sequence offsets for every sequence starting in this tile
         for (uint32_t i = lb + tid; i < ub; i += NT) {
-            const uint64_t so = A.seq_off[i];
+            const uint64_t so = i - lb < (uint32_t)SOC ? S.soc[i - lb + 1] : A.seq_off[i];
             const uint32_t x = (uint32_t)((int64_t)so - W0);
             const uint32_t qx = S.qoff[x >> 5] + __popc(S.keepw[x >> 5] & lowmask(x & 31));
             const uint32_t v = qx - (uint32_t)hk;
@@ -769,6 +777,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         par ^= 1;
         PHASE(8);
     }
+    if (tid == 0 && A.region_cap) atomicAdd(A.cursor, S.cur);     // the host reads the total from the cursor
     PHASE_FLUSH;
 }
 
