@@ -493,7 +493,13 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
         if (n_min > 0) {
             const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 16);
-            S2K_LAUNCH(k_windows, g3, 256, 0, st, false, C);
+            switch (P.k <= (uint32_t)KW_MAX ? (int)P.k : 0) {
+#define S2K_WINDOWS_CASE(K) case K: S2K_LAUNCH(k_windows_w<K>, g3, 256, 0, st, false, C); break;
+                S2K_WINDOWS_CASE(1) S2K_WINDOWS_CASE(2) S2K_WINDOWS_CASE(3) S2K_WINDOWS_CASE(4) S2K_WINDOWS_CASE(5) S2K_WINDOWS_CASE(6)
+                S2K_WINDOWS_CASE(7) S2K_WINDOWS_CASE(8) S2K_WINDOWS_CASE(9) S2K_WINDOWS_CASE(10) S2K_WINDOWS_CASE(11) S2K_WINDOWS_CASE(12)
+#undef S2K_WINDOWS_CASE
+                default: S2K_LAUNCH(k_windows, g3, 256, 0, st, false, C);
+            }
             CU(cudaGetLastError());
             ctx->launches += 1;
         }

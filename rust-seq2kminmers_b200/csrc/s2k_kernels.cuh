@@ -1038,6 +1038,57 @@ __global__ void __launch_bounds__(256) k_windows(const __grid_constant__ K3Args 
     }
 }
 
+// Warp-cooperative form for small k (the usual 3..10): every lane loads ONE record and mixes its hash once; the k
+// values of a window come from the k-1 lanes above by shuffle, with compile-time rotation amounts.  A warp pass covers
+// 32 consecutive minimizers and emits the 32-(k-1) windows that start in its first lanes.  (k_windows recomputes
+// mix() k times per item and rotates by run-time amounts: ~190 instructions per item against ~90 here.)
+template <int R> __device__ __forceinline__ uint64_t rol64c(uint64_t x)
+{
+    constexpr int r = R & 63;
+    return r ? ((x << r) | (x >> (64 - r))) : x;
+}
+template <int K, int T> struct WindowFold {
+    static __device__ __forceinline__ void run(uint64_t m, uint64_t &f, uint64_t &r)
+    {
+        const uint64_t mt = T ? __shfl_down_sync(0xffffffffu, m, T) : m;
+        f ^= rol64c<K - 1 - T>(mt);
+        r ^= rol64c<T>(mt);
+        WindowFold<K, T + 1>::run(m, f, r);
+    }
+};
+template <int K> struct WindowFold<K, K> {
+    static __device__ __forceinline__ void run(uint64_t, uint64_t &, uint64_t &) {}
+};
+template <int K>
+__global__ void __launch_bounds__(256) k_windows_w(const __grid_constant__ K3Args A)
+{
+    constexpr uint32_t OUT = 32 - (K - 1);                  // windows emitted per warp pass
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_pass = (A.n_min + OUT - 1) / OUT;
+    for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_pass; p += nwarps) {
+        const uint64_t g = p * OUT + lane;
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+        if (g < A.n_min) rec = A.mins[g];
+        uint64_t f = 0, r = 0;
+        WindowFold<K, 0>::run(mix32(rec.x), f, r);
+        const uint32_t end = K > 1 ? __shfl_down_sync(0xffffffffu, rec.z, K - 1) : rec.z;
+        if (lane < OUT && g < A.n_min) {
+            const uint32_t rid = rec.w;
+            const uint64_t c = g - A.min_off[rid];          // window index inside the sequence == offset
+            const uint64_t k0 = A.km_off[rid];
+            if (c < A.km_off[rid + 1] - k0) {               // else: fewer than k minimizers left (or tail rule)
+                const uint64_t o = k0 + c;
+                A.hash[o] = f < r ? f : r;
+                A.start[o] = rec.y;
+                A.end[o] = end;
+                A.rev[o] = r < f;
+            }
+        }
+    }
+}
+constexpr int KW_MAX = 12;          // largest k with a k_windows_w instantiation
+
 // ------------------------------------------------------------------------------------------------ RLE (encode_rle_simd)
 // src/hpc.rs:44-147 over a batch: kept bytes + run starts, ordered.  Same keep rule and tile order machinery,
 // no hashing.  One thread handles 32 bases; ordered by a decoupled look-back on kept counts.

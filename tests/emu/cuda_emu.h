@@ -107,6 +107,11 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, int o)
     const int lane = (int)(threadIdx.x & 31);
     return emu_warp_exchange(v, lane - o, lane >= o);
 }
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, int o)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    return emu_warp_exchange(v, lane + o, lane + o < 32);
+}
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int o)
 {
     const int lane = (int)(threadIdx.x & 31);
