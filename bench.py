@@ -186,6 +186,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = S.Context(local_rank)
     ctx.set_timing(True)
+    # Host transport per rank (s2k_ctx_set_transport): packing pays while a GPU's own PCIe link is the limit; with
+    # several ranks on one host the host's memory bandwidth is, and packing only adds traffic.
+    pack_threads, pack_ratio = (0, 0.7) if world == 1 else ((6, 0.5) if world == 2 else (0, 0.0))
+    ctx.set_transport(pack_threads, pack_ratio)
     split_one = args.workload == "c4" and world > 1    # one sequence cut into base ranges: strong scaling
     sharding = importlib.import_module("rust-seq2kminmers_b200.sharding")
     if split_one:
@@ -291,7 +295,7 @@ def main():
                "host_input_bytes_per_step": n_bases + 8 * (n_reads + 1),
                "d2h_bytes_per_step": 17 * int(out.n_items) + 8 * (n_reads + 1) * 2 + 4 * n_reads,
                "steps": e_steps, "api": "s2k_run (C ABI, pinned host ASCII buffers in, pinned host items out)",
-               "transport": f"{n_packed} slabs packed to 2 bits/base by host threads + {n_plain} slabs as plain ASCII (s2k_ctx_set_transport default)"}
+               "transport": f"{n_packed} slabs packed to 2 bits/base by host threads + {n_plain} slabs as plain ASCII (s2k_ctx_set_transport: threads {pack_threads or 'default'}, ratio {pack_ratio})"}
         # the same with the 2-bit transport switched off: every byte crosses PCIe as ASCII
         ctx.set_transport(0, 0.0)
         ctx.run(hb_np, hso_np, L_PARAM, K_PARAM, DENSITY, S.HashMode(mode), S.HashVariant(variant), copy=False, no_tail_rule=split_one)
@@ -304,7 +308,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
         e2e["plain_ascii_transport_value"] = (L if split_one else world * n_bases) * 2 / float(tt2.item()) / 1e9
-        ctx.set_transport(0, 0.7)
+        ctx.set_transport(pack_threads, pack_ratio)
         del hb, hso
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
