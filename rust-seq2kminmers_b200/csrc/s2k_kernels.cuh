@@ -107,6 +107,8 @@ struct K1Args {
 };
 
 struct Smem {
+    uint8_t  pre[16];                        // stays ZC8: with l = 255 and owner space shifted 3 bases into the halo the
+                                             // word-wise hash stage reads up to 4 bytes below code[0]
     uint8_t  code[XB + WIN + 128];           // 8*class of every kept base, index XB + (kept index in the window)
     unsigned long long hitw[2][NT + 1][MW];  // per pass, per thread: selected owners (bit i = owner CH*t + i)
     uint32_t hitpre[2][NT + 1];              // ... and how many hits precede that thread in the tile
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     if (tid < XYN) S.xy[tid] = A.xy[tid];
     if (tid < XFN) { S.xf[tid] = A.xf[tid]; S.x2[tid] = A.x2[tid]; }
     for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
+    if (tid < 16) S.pre[tid] = ZC8;
     for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
     for (int i = tid; i < FW; i += NT) { S.f1[i] = 0; S.f2[i] = 0; }
     if (tid == 0) { S.n_dirty[0] = 0; S.n_dirty[1] = 0; }
