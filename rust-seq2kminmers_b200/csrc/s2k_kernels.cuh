@@ -125,7 +125,7 @@ struct Smem {
     alignas(128) uint2 xf[XFN];              // 128-byte aligned: the 16 live entries cover the 32 banks once
     alignas(128) uint2 x2[XFN];
     uint8_t  lut[256];
-    uint32_t wsum[8];
+    uint32_t wsum[3][NT / 32];               // warp totals: kept-count scan, hit-count scan of pass 0 / pass 1
     uint32_t hk;
     uint32_t next[2];                        // tile ticket by parity: the next one is drawn while this one is processed
     uint32_t nlb[2][2];                      // ... with its tile_lb pair
@@ -170,11 +170,11 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v)
     return v;
 }
 // Exclusive block scan of one uint32 per thread (NT threads). Returns exclusive prefix; total via out-param.
+// One barrier: the caller hands in a wsum buffer whose previous readers are already behind some other barrier.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, uint32_t &total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = warp_incl_scan(v, lane);
-    __syncthreads();                       // previous users of wsum are done
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     uint32_t pre = 0, tot = 0;
@@ -513,12 +513,23 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             klo &= (uint32_t)vmask; khi &= (uint32_t)(vmask >> 32);
         }
         const uint32_t clo = __popc(klo);
-        uint32_t wk;
-        const uint32_t q = block_excl_scan(clo + __popc(khi), S.wsum, wk);
+        // The thread that holds the halo/tile boundary sits in warp 0 (halo <= 512 raw bases = 8 threads): its prefix
+        // needs no warp totals, so the kept count of the halo is published before the scan's only barrier.
+        const uint32_t cnt_kept = clo + __popc(khi);
+        const uint32_t incl_kept = warp_incl_scan(cnt_kept, lane);
+        if (lane == 31) S.wsum[0][warp] = incl_kept;
+        if (tid == (int)(A.halo >> 6)) S.hk = incl_kept - cnt_kept + (((A.halo >> 5) & 1u) ? clo : 0u);
+        __syncthreads();
+        uint32_t q = incl_kept - cnt_kept, wk = 0;
+#pragma unroll
+        for (int i = 0; i < NT / 32; ++i) {
+            const uint32_t sw = S.wsum[0][i];
+            if (i < warp) q += sw;
+            wk += sw;
+        }
         S.keepw[2 * tid] = klo; S.keepw[2 * tid + 1] = khi;
         S.qoff[2 * tid] = q; S.qoff[2 * tid + 1] = q + clo;
         if (tid == NT - 1) { S.qoff[NCHUNK] = wk; S.keepw[NCHUNK] = 0; }
-        if (tid == (int)(A.halo >> 6)) S.hk = ((A.halo >> 5) & 1u) ? q + clo : q;
         for (uint32_t m = (q + 63u) & ~63u; m < q + clo + __popc(khi); m += 64)
             S.qmap[m >> 6] = (uint16_t)(m < q + clo ? 2 * tid : 2 * tid + 1);
 
@@ -548,7 +559,6 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             }
         }
         if (tid == 0) S.next[par ^ 1] = t_next;           // the ticket drawn at the top has long arrived
-        __syncthreads();
         PHASE(3);
         // Owner space starts up to 3 kept bases inside the halo (those pseudo-owners are masked out below) so that
         // every thread's class bytes begin on a word boundary of S.code: the hash stage reads them as words.
@@ -666,7 +676,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 #pragma unroll
             for (int x = 0; x < MW; ++x) cnt += __popcll(mask[x]);
             uint32_t tot;
-            const uint32_t ex = block_excl_scan(cnt, S.wsum, tot);
+            const uint32_t ex = block_excl_scan(cnt, S.wsum[1 + pass], tot);
 #pragma unroll
             for (int x = 0; x < MW; ++x) S.hitw[pass][tid][x] = mask[x];
             S.hitpre[pass][tid] = tile_min + ex;
@@ -705,10 +715,11 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         PHASE(6);
 
         // ---- S7: ordered hit list in shared memory, then one thread per minimizer
+        const int n_pass = n_own > (uint32_t)CAP ? 2 : 1;  // the second pass exists for badly compressing HPC tiles only
         for (uint32_t base = 0; base < tile_min; base += HL) {
             if (base) __syncthreads();                     // previous round has been consumed
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < n_pass; ++pass) {
                 uint32_t o = S.hitpre[pass][tid];
 #pragma unroll
                 for (int x = 0; x < MW; ++x) {
