@@ -490,15 +490,18 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // ---- S3b: keep mask, block scan of kept counts
         uint32_t klo, khi;
         if (HPC) {
-            uint32_t prevb = __shfl_up_sync(0xffffffffu, w[15] >> 24, 1);
-            if (lane == 0) prevb = (g0 > 0 && g0 <= (int64_t)A.n_bases) ? A.bases[g0 - 1] : 0u;
+            // keep bit = byte differs from the byte before it.  Per word: PRMT lines the previous bytes up, XOR, the
+            // classic "byte is non-zero" carry trick leaves bit 7 of each byte, one multiply gathers the four bits into
+            // the top nibble and a funnel shift appends it -- words are visited from high to low so that base 0 ends up
+            // in bit 0.
+            uint32_t prevw = __shfl_up_sync(0xffffffffu, w[15], 1);
+            if (lane == 0) prevw = ((g0 > 0 && g0 <= (int64_t)A.n_bases) ? (uint32_t)A.bases[g0 - 1] : 0u) << 24;
             uint32_t kk[2] = {0u, 0u};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t sh = (w[i] << 8) | prevb;
-                prevb = w[i] >> 24;
-                const uint32_t neq = __vcmpne4(w[i], sh);
-                kk[i >> 3] |= (((neq & 0x08040201u) * 0x01010101u) >> 24) << (4 * (i & 7));
+            for (int i = 15; i >= 0; --i) {
+                const uint32_t x = w[i] ^ __byte_perm(i ? w[i - 1] : prevw, w[i], 0x6543u);
+                const uint32_t nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+                kk[i >> 3] = __funnelshift_l(nz * 0x00204081u, kk[i >> 3], 4);
             }
             klo = kk[0] | S.startw[2 * tid];
             khi = kk[1] | S.startw[2 * tid + 1];
