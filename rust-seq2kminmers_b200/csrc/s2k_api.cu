@@ -192,15 +192,21 @@ uint64_t pack2_avx512(const uint8_t *src, uint8_t *dst, size_t n)      // n mult
     const __m512i three = _mm512_set1_epi8(3);
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
     const __m512i m1 = _mm512_set1_epi16(0x0401), m2 = _mm512_set1_epi32(0x00100001);
-    uint64_t bad = 0;
+    __mmask64 bad = 0;
+    // dst is 16-byte aligned here (slab staging buffers, 64-base granules): streaming stores keep the packed bytes out
+    // of the caches and spare the read-for-ownership -- the packers are bound by host memory traffic, not by arithmetic
+    const bool nt = ((uintptr_t)dst & 15) == 0;
     for (size_t i = 0; i < n; i += 64) {
         const __m512i v = _mm512_loadu_si512(src + i);
         const __m512i c = _mm512_and_si512(_mm512_srli_epi16(v, 1), three);
-        bad += (uint64_t)__builtin_popcountll(_mm512_cmpneq_epi8_mask(_mm512_shuffle_epi8(lut, c), v));
+        bad |= _mm512_cmpneq_epi8_mask(_mm512_shuffle_epi8(lut, c), v);
         const __m512i p32 = _mm512_madd_epi16(_mm512_maddubs_epi16(c, m1), m2);     // c0 + 4 c1 + 16 c2 + 64 c3 per 4 bases
-        _mm_storeu_si128((__m128i *)(dst + (i >> 2)), _mm512_cvtepi32_epi8(p32));
+        const __m128i o = _mm512_cvtepi32_epi8(p32);
+        if (nt) _mm_stream_si128((__m128i *)(dst + (i >> 2)), o);
+        else _mm_storeu_si128((__m128i *)(dst + (i >> 2)), o);
     }
-    return bad;
+    if (nt) _mm_sfence();
+    return bad != 0;
 }
 #endif
 uint64_t pack2_range(const uint8_t *src, uint8_t *dst, size_t lo, size_t hi)   // lo multiple of 64; packs bases [lo, hi)

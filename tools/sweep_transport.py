@@ -19,8 +19,8 @@ def main():
     print("host cores", os.cpu_count(), flush=True)
     def run():
         return ctx.run(hb_np, hso, 31, 5, 0.01, S.HashMode.HpcSimd, S.HashVariant.NT1_32, copy=False)
-    for slab_mib, thr, ratio in itertools.product((128, 256, 512), (4, 8, 12, 16), (0.0, 0.5, 0.7, 0.85, 1.0)):
-        if ratio == 0.0 and thr != 4: continue
+    for slab_mib, thr, ratio in itertools.product((256,), (10, 12, 14), (0.0, 0.5, 0.6, 0.7, 0.8)):
+        if ratio == 0.0 and thr != 10: continue
         ctx.set_slab_bytes(slab_mib << 20); ctx.set_transport(thr, ratio)
         run(); torch.cuda.synchronize()
         t0 = time.perf_counter()
