@@ -100,6 +100,7 @@ struct s2k_ctx {
     bool pipe_ready = false;
     uint64_t slab_bytes = 0;        // 0 = default
     Buf d_in[2], d_in_off[2], h_off_stage[2];
+    Buf d_piece, h_piece;           // long sequences in pieces: kept-base counter and cut results
     Buf d_pack[2], h_pack[3];       // 2-bit transport: device landing buffers, ring of pinned staging buffers
     cudaEvent_t ev_pack[3] = {nullptr, nullptr, nullptr};
     int host_threads = 0;           // 0 = 3/4 of the hardware threads, at most 16 (measured best on a 16-core host)
@@ -173,6 +174,8 @@ void release(Buf &b)
 #include <immintrin.h>
 #endif
 #include <atomic>
+#include <chrono>
+#include <thread>
 namespace {
 
 // ---- 2-bit transport: host side.  Packs n bases (4 per byte, code (b>>1)&3: A0 C1 T2 G3) and counts the bytes that
@@ -610,7 +613,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
                   &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in_off[0], &ctx->d_in_off[1],
-                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1],
+                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->d_piece, &ctx->h_piece, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1],
                   &ctx->h_pack[0], &ctx->h_pack[1], &ctx->h_pack[2]};
     for (Buf *b : all) release(*b);
     if (ctx->tm.created) {
@@ -730,13 +733,48 @@ int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes)
     return S2K_OK;
 }
 
-// Large host batches: slabs cut at sequence boundaries flow through H2D -> kernels -> D2H on three streams, so that
-// both PCIe directions and the compute overlap.  Input slabs are double-buffered on the device; the device result
-// buffers are single (a slab's D2H is long finished when the next slab's H2D completes).
+// Large host batches: slabs flow through H2D -> kernels -> D2H on three streams, so that both PCIe directions and the
+// compute overlap.  Input slabs are double-buffered on the device; the device result buffers are single (a slab's D2H
+// is long finished when the next slab's H2D completes).
+//
+// A slab is a run of whole sequences, or a PIECE of one long sequence (longer than 1.5 slabs; a chromosome).  A piece
+// owns the raw range [b0, b1) and is resident with a right overlap, [b0, hi): it runs as a sequence of its own (tail
+// rule off) and keeps the minimizers that start in its range and the k-min-mers whose first minimizer it owns -- an
+// l-mer depends on its own bases only, so nothing to the left is needed once the cut sits on a homopolymer-run boundary,
+// and the overlap holds the k-1 further minimizers of the windows that begin near b1 (checked; if some stretch is so
+// poor in minimizers that it does not, the batch is redone with an 8 times larger overlap).  The AVX-512 tail rule
+// (src/nthash_avx512_32.rs:134-138) is a property of the whole sequence: kept bases are counted per piece and the last
+// piece drops the minimizers ending in the final 16 kept bases when the rule fires.  (The multi-GPU split of one
+// sequence, sharding.py, follows the same ownership rule.)
+static std::atomic<long> g_stage{0}, g_aux{0};
+static void stage_watchdog()
+{
+    static std::atomic<bool> started{false};
+    if (!getenv("S2K_WATCHDOG") || started.exchange(true)) return;
+    std::thread([]() {
+        long last = -1;
+        for (;;) {
+            std::this_thread::sleep_for(std::chrono::seconds(5));
+            const long st_now = g_stage.load();
+            if (st_now == last && st_now != 0 && st_now != 600000)
+                fprintf(stderr, "[s2k watchdog] run_pipelined has been at stage %ld (aux %ld) for 5 s\n", st_now, g_aux.load());
+            last = st_now;
+        }
+    }).detach();
+}
+#define STAGE(x) g_stage.store(x)
+struct Slab {
+    uint64_t r0, r1;              // sequences [r0, r1); a piece: r1 = r0 + 1
+    bool piece, first, last;      // piece of sequence r0; first / last piece of it
+    uint64_t b0, b1, hi;          // absolute offsets into `bases`: first base copied, end of the owned range, end of the copy
+};
 static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const Plan &P,
-                         uint64_t slab_bytes, s2k_result *out)
+                         uint64_t slab_bytes, uint64_t overlap, bool &overlap_short, s2k_result *out)
 {
     int rc;
+    overlap_short = false;
+    stage_watchdog();
+    STAGE(1);
     if (!ctx->pipe_ready) {
         CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -748,20 +786,49 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     cudaStream_t st = ctx->stream;
     const uint64_t n_bases = seq_off[n_seqs];
     const bool want_min = (ctx->flags & S2K_WANT_MINIMIZERS) != 0;
-    // slab boundaries (sequence indices)
-    std::vector<uint64_t> cut{0};
+    Plan PP = P;                                           // pieces: the tail rule is applied here, not by the kernels
+    PP.quirk = false;
+    // slab plan
+    std::vector<Slab> slabs;
     uint64_t max_b = 0, max_n = 0;
-    while (cut.back() < n_seqs) {
-        const uint64_t r0 = cut.back();
-        const uint64_t *e = std::upper_bound(seq_off + r0 + 1, seq_off + n_seqs + 1, seq_off[r0] + slab_bytes);
-        uint64_t r1 = (uint64_t)(e - seq_off) - 1;
-        if (r1 <= r0) r1 = r0 + 1;                       // a sequence longer than a slab travels whole
-        if (r1 > n_seqs) r1 = n_seqs;
-        cut.push_back(r1);
-        max_b = std::max(max_b, seq_off[r1] - seq_off[r0]);
+    bool any_piece = false;
+    for (uint64_t r0 = 0; r0 < n_seqs;) {
+        const uint64_t len0 = seq_off[r0 + 1] - seq_off[r0];
+        if (len0 > slab_bytes + slab_bytes / 2 && len0 > (uint64_t)P.l) {
+            const uint64_t s0 = seq_off[r0], s1 = seq_off[r0 + 1];
+            uint64_t b0 = s0;
+            while (b0 < s1) {
+                uint64_t b1 = std::min(s1, b0 + std::min<uint64_t>(slab_bytes, 1ull << 31));
+                if (s1 - b1 < slab_bytes / 2) b1 = s1;                          // no tiny last piece
+                if (P.hpc) while (b1 < s1 && bases[b1] == bases[b1 - 1]) ++b1;  // cut on a run boundary
+                const uint64_t hi = b1 == s1 ? s1 : std::min(s1, b1 + overlap);
+                slabs.push_back(Slab{r0, r0 + 1, true, b0 == s0, b1 == s1, b0, b1, hi});
+                max_b = std::max(max_b, hi - b0);
+                b0 = b1;
+            }
+            max_n = std::max<uint64_t>(max_n, 1);
+            any_piece = true;
+            ++r0;
+            continue;
+        }
+        uint64_t r1 = r0, nb = 0;
+        while (r1 < n_seqs) {
+            const uint64_t len = seq_off[r1 + 1] - seq_off[r1];
+            if (len > slab_bytes + slab_bytes / 2 && len > (uint64_t)P.l) break;            // a long one: pieces
+            if (r1 > r0 && nb + len > slab_bytes) break;
+            nb += len; ++r1;
+        }
+        slabs.push_back(Slab{r0, r1, false, false, false, seq_off[r0], seq_off[r1], seq_off[r1]});
+        max_b = std::max(max_b, nb);
         max_n = std::max(max_n, r1 - r0);
+        r0 = r1;
     }
-    const size_t n_slabs = cut.size() - 1;
+    if (any_piece) {
+        if ((rc = ensure(ctx, ctx->d_piece, 64, false))) return rc;
+        if ((rc = ensure(ctx, ctx->h_piece, 64, true))) return rc;
+        for (int i = 0; i < 2; ++i) if ((rc = ensure(ctx, ctx->h_off_stage[i], 16, true))) return rc;
+    }
+    const size_t n_slabs = slabs.size();
     for (int i = 0; i < 2; ++i) {
         if ((rc = ensure(ctx, ctx->d_in[i], max_b + 16, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_in_off[i], (max_n + 1) * 8, false))) return rc;
@@ -808,7 +875,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
                         std::this_thread::yield();
                     }
                     const size_t sl = packed_slabs[ps];
-                    const uint64_t b0 = seq_off[cut[sl]], nb = seq_off[cut[sl + 1]] - b0;
+                    const uint64_t b0 = slabs[sl].b0, nb = slabs[sl].hi - b0;
                     const uint64_t chunk = ((nb + T - 1) / T + 63) & ~uint64_t(63);
                     const uint64_t lo = std::min<uint64_t>(nb, chunk * wi), hi = std::min<uint64_t>(nb, lo + chunk);
                     if (hi > lo) pk_bad[ps].fetch_add(pack2_range(bases + b0, ptr<uint8_t>(ctx->h_pack[ps % 3]), lo, hi));
@@ -824,13 +891,22 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
 
     auto issue_h2d = [&](size_t s) -> int {
         const int b = (int)(s & 1);
-        const uint64_t r0 = cut[s], r1 = cut[s + 1], nb = seq_off[r1] - seq_off[r0];
+        const Slab &L = slabs[s];
+        const uint64_t r0 = L.r0, r1 = L.r1, nb = L.hi - L.b0;
         const int ps = ps_of[s];
         bool packed = false;
         if (ps >= 0) {
-            while (pk_done[ps].load(std::memory_order_acquire) < (uint32_t)T) { poll_release(); std::this_thread::yield(); }
+            STAGE(100000 + (long)s); g_aux.store(ps * 1000 + (long)pk_released.load());
+            const auto t_wait = std::chrono::steady_clock::now();
+            while (pk_done[ps].load(std::memory_order_acquire) < (uint32_t)T) {
+                poll_release();
+                std::this_thread::yield();
+                if (std::chrono::steady_clock::now() - t_wait > std::chrono::seconds(120))      // never seen; fail, do not hang
+                    return fail(ctx, S2K_ERR_INTERNAL, "2-bit transport: host packers stalled");
+            }
             packed = nb > 0 && pk_bad[ps].load() == 0;
         }
+        STAGE(200000 + (long)s);
         CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_free[b], 0));          // the kernels of slab s-2 are done with it
         ctx->tr_h2d_bytes += (packed ? (nb + 3) / 4 : nb) + (r1 - r0 + 1) * 8;
         if (packed) ++ctx->tr_packed; else ++ctx->tr_plain;
@@ -843,17 +919,23 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             ctx->launches += 1;
         } else {
             if (ps >= 0) pk_state[ps] = 2;
-            if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, bases + seq_off[r0], nb, cudaMemcpyHostToDevice, ctx->s_h2d));
+            if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, bases + L.b0, nb, cudaMemcpyHostToDevice, ctx->s_h2d));
         }
         poll_release();
-        // offsets: copy the caller's slice as it is, rebase it to the slab on the device
         uint64_t *d_off = ptr<uint64_t>(ctx->d_in_off[b]);
-        CU(cudaMemcpyAsync(d_off, seq_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
-        if (r0) {
-            const int g = (int)std::min<uint64_t>((r1 - r0 + 256) / 256, (uint64_t)ctx->sm_count * 4);
-            S2K_LAUNCH(k_sub_first, g, 256, 0, ctx->s_h2d, false, d_off, r1 - r0 + 1);
-            S2K_LAUNCH(k_zero_first, 1, 1, 0, ctx->s_h2d, false, d_off);
-            ctx->launches += 2;
+        if (L.piece) {                                                    // the piece is a sequence of its own: {0, nb}
+            uint64_t *h_off = ptr<uint64_t>(ctx->h_off_stage[b]);         // free again: slab s-2 has been through the kernels
+            h_off[0] = 0; h_off[1] = nb;
+            CU(cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, ctx->s_h2d));
+        } else {
+            // offsets: copy the caller's slice as it is, rebase it to the slab on the device
+            CU(cudaMemcpyAsync(d_off, seq_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+            if (r0) {
+                const int g = (int)std::min<uint64_t>((r1 - r0 + 256) / 256, (uint64_t)ctx->sm_count * 4);
+                S2K_LAUNCH(k_sub_first, g, 256, 0, ctx->s_h2d, false, d_off, r1 - r0 + 1);
+                S2K_LAUNCH(k_zero_first, 1, 1, 0, ctx->s_h2d, false, d_off);
+                ctx->launches += 2;
+            }
         }
         CU(cudaEventRecord(ctx->ev_in[b], ctx->s_h2d));
         return S2K_OK;
@@ -865,30 +947,96 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     CU(cudaEventRecord(ctx->ev_free[1], st));
     CU(cudaEventRecord(ctx->ev_out, ctx->s_d2h));
     if ((rc = issue_h2d(0))) return rc;
+    uint64_t seq_cnt = 0, kept_plain = 0;                  // running values of the long sequence being pieced together
     for (size_t s = 0; s < n_slabs; ++s) {
         const int b = (int)(s & 1);
-        const uint64_t r0 = cut[s], r1 = cut[s + 1], ns = r1 - r0, nb = seq_off[r1] - seq_off[r0];
+        const Slab &L = slabs[s];
+        const uint64_t r0 = L.r0, r1 = L.r1, ns = r1 - r0, nb = L.hi - L.b0;
         if (s + 1 < n_slabs) {
             if ((rc = issue_h2d(s + 1))) return rc;
         }
         CU(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));                    // inputs of this slab have landed
         CU(cudaStreamWaitEvent(st, ctx->ev_out, 0));                      // results of the previous slab have left
         s2k_result dev;
-        rc = run_device(ctx, ptr<uint8_t>(ctx->d_in[b]), ptr<uint64_t>(ctx->d_in_off[b]), ns, nb, P, st, &dev);
+        STAGE(300000 + (long)s);
+        rc = run_device(ctx, ptr<uint8_t>(ctx->d_in[b]), ptr<uint64_t>(ctx->d_in_off[b]), ns, nb, L.piece ? PP : P, st, &dev);
         if (rc != S2K_OK) return rc;
-        // per-slab prefixes / sequence indices -> global
-        const int g1 = (int)std::min<uint64_t>((ns + 256) / 256, (uint64_t)ctx->sm_count * 8);
-        if (items) S2K_LAUNCH(k_add_u64, g1, 256, 0, st, false, const_cast<uint64_t *>(dev.km_off), ns + 1, items);
-        if (mins) S2K_LAUNCH(k_add_u64, g1, 256, 0, st, false, const_cast<uint64_t *>(dev.min_off), ns + 1, mins);
-        if (want_min && r0 && dev.n_minimizers) {
-            const int g2 = (int)std::min<uint64_t>((dev.n_minimizers + 255) / 256, (uint64_t)ctx->sm_count * 8);
-            S2K_LAUNCH(k_add_seq, g2, 256, 0, st, false, reinterpret_cast<uint4 *>(const_cast<s2k_minimizer *>(dev.minimizers)),
-                       dev.n_minimizers, (uint32_t)r0);
+        STAGE(400000 + (long)s);
+        uint64_t ni = dev.n_items, nm = dev.n_minimizers;
+        if (!L.piece) {
+            // per-slab prefixes / sequence indices -> global
+            const int g1 = (int)std::min<uint64_t>((ns + 256) / 256, (uint64_t)ctx->sm_count * 8);
+            if (items) S2K_LAUNCH(k_add_u64, g1, 256, 0, st, false, const_cast<uint64_t *>(dev.km_off), ns + 1, items);
+            if (mins) S2K_LAUNCH(k_add_u64, g1, 256, 0, st, false, const_cast<uint64_t *>(dev.min_off), ns + 1, mins);
+            if (want_min && r0 && dev.n_minimizers) {
+                const int g2 = (int)std::min<uint64_t>((dev.n_minimizers + 255) / 256, (uint64_t)ctx->sm_count * 8);
+                S2K_LAUNCH(k_add_seq, g2, 256, 0, st, false, reinterpret_cast<uint4 *>(const_cast<s2k_minimizer *>(dev.minimizers)),
+                           dev.n_minimizers, (uint32_t)r0);
+            }
+        } else {
+            // ---- a piece of a long sequence: what it owns, tail rule, coordinates of the whole sequence
+            unsigned long long *dp = ptr<unsigned long long>(ctx->d_piece), *hp = ptr<unsigned long long>(ctx->h_piece);
+            const uint64_t s0 = seq_off[r0], s1 = seq_off[r0 + 1], own = L.b1 - L.b0, n_min = dev.n_minimizers;
+            uint4 *dmins = reinterpret_cast<uint4 *>(const_cast<s2k_minimizer *>(dev.minimizers));
+            if (L.first) {
+                seq_cnt = 0; kept_plain = 0;
+                ptr<uint64_t>(ctx->h_km_off)[r0] = items;
+                ptr<uint64_t>(ctx->h_min_off)[r0] = mins;
+                CU(cudaMemsetAsync(dp, 0, 8, st));
+            }
+            if (P.quirk) {
+                if (P.hpc) {
+                    const int g = (int)std::min<uint64_t>((own + 255) / 256, (uint64_t)ctx->sm_count * 16);
+                    if (own) S2K_LAUNCH(k_count_kept, g, 256, 0, st, false, ptr<uint8_t>(ctx->d_in[b]), own, dp);
+                } else kept_plain += own;
+            }
+            bool rule = false;
+            uint64_t e16 = 0xffffffffull;
+            if (L.last && P.quirk) {
+                uint64_t kept_total = kept_plain;
+                if (P.hpc) {
+                    CU(cudaMemcpyAsync(hp, dp, 8, cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                    kept_total = hp[0];
+                }
+                const uint64_t S = kept_total >= P.l ? kept_total - P.l + 1 : 0;
+                rule = S > 16 && S % 16 == 0;
+                if (rule) {                                               // 16th kept base from the end of the sequence
+                    uint64_t pos = s1, left = 16;
+                    while (left && pos > s0) { --pos; if (!P.hpc || pos == s0 || bases[pos] != bases[pos - 1]) --left; }
+                    if (pos <= L.b0) { overlap_short = true; return S2K_OK; }   // a homopolymer tail as long as a piece
+                    e16 = pos - L.b0;
+                }
+            }
+            S2K_LAUNCH(k_piece_cut, 1, 1, 0, st, false, dmins, n_min, L.last ? 0xffffffffu : (uint32_t)own, (uint32_t)e16, dp + 2);
+            CU(cudaMemcpyAsync(hp + 2, dp + 2, 16, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            ctx->launches += 2;
+            const uint64_t n_keep = rule ? hp[3] : n_min;
+            const uint64_t i1 = L.last ? n_keep : hp[2];
+            if (!L.last && i1 + P.k + 3 > n_min) { overlap_short = true; return S2K_OK; }   // windows near b1 lack followers
+            const uint64_t n_win = n_keep >= P.k ? n_keep - P.k + 1 : 0;
+            ni = std::min(i1, n_win);
+            nm = L.last ? n_min : i1;
+            seq_cnt += i1;
+            const uint32_t add = (uint32_t)(L.b0 - s0);
+            if (add && ni) {
+                const int g = (int)std::min<uint64_t>((ni + 255) / 256, (uint64_t)ctx->sm_count * 8);
+                S2K_LAUNCH(k_piece_shift_items, g, 256, 0, st, false, const_cast<uint32_t *>(dev.start), const_cast<uint32_t *>(dev.end), ni, add);
+            }
+            if (want_min && nm && (add || r0)) {
+                const int g = (int)std::min<uint64_t>((nm + 255) / 256, (uint64_t)ctx->sm_count * 8);
+                S2K_LAUNCH(k_piece_shift_mins, g, 256, 0, st, false, dmins, nm, add, (uint32_t)r0);
+            }
+            if (L.last) {
+                ptr<uint64_t>(ctx->h_km_off)[r0 + 1] = items + ni;
+                ptr<uint64_t>(ctx->h_min_off)[r0 + 1] = mins + nm;
+                ptr<uint32_t>(ctx->h_min_cnt)[r0] = (uint32_t)seq_cnt;
+            }
         }
         CU(cudaEventRecord(ctx->ev_free[b], st));
         CU(cudaEventRecord(ctx->ev_done, st));
         // host result buffers: sized from the first slab's rates, grown (rarely) if a later slab is denser
-        const uint64_t ni = dev.n_items, nm = dev.n_minimizers;
         uint64_t need_i = items + ni, need_m = mins + nm;
         if (s == 0 && nb) {
             const double scale = (double)n_bases / (double)nb * 1.03;
@@ -912,18 +1060,22 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_end) + items, dev.end, ni * 4, cudaMemcpyDeviceToHost, so));
             CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_rev) + items, dev.rev, ni, cudaMemcpyDeviceToHost, so));
         }
-        const uint64_t tail = (s + 1 == n_slabs) ? 1 : 0;                  // the last slab also brings the final prefix
-        CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_km_off) + r0, dev.km_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
-        CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_min_off) + r0, dev.min_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
-        if (ns) CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_min_cnt) + r0, dev.min_cnt, ns * 4, cudaMemcpyDeviceToHost, so));
+        if (!L.piece) {
+            const uint64_t tail = (s + 1 == n_slabs) ? 1 : 0;              // the last slab also brings the final prefix
+            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_km_off) + r0, dev.km_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_min_off) + r0, dev.min_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
+            if (ns) CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_min_cnt) + r0, dev.min_cnt, ns * 4, cudaMemcpyDeviceToHost, so));
+        }
         if (want_min && nm)
             CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_mins) + mins * 16, dev.minimizers, nm * 16, cudaMemcpyDeviceToHost, so));
         CU(cudaEventRecord(ctx->ev_out, so));
         items += ni; mins += nm;
         poll_release();
     }
+    STAGE(500000);
     CU(cudaStreamSynchronize(ctx->s_d2h));
     CU(cudaStreamSynchronize(ctx->s_h2d));
+    STAGE(600000);
     std::memset(out, 0, sizeof(*out));
     out->n_seqs = n_seqs; out->n_items = items; out->n_minimizers = mins;
     out->location = S2K_LOC_HOST;
@@ -954,7 +1106,20 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
     cudaStream_t st = ctx->stream;
     {
         const uint64_t slab = ctx->slab_bytes ? ctx->slab_bytes : (256ull << 20);
-        if (n_bases > slab + slab / 2 && n_seqs > 1) return run_pipelined(ctx, bases, seq_off, n_seqs, P, slab, out);
+        if (n_bases > slab + slab / 2 && n_seqs >= 1) {
+            // right overlap of a piece of a long sequence: room for k-1 further minimizers at the selection rate, with a
+            // wide margin (checked per piece; grown and redone if some stretch of the sequence is poorer than that)
+            const double frac = std::max(1e-9, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+            uint64_t overlap = (uint64_t)std::min(4.0e9, 64.0 * (P.k + 8.0) / frac + 64.0 * P.l + 4096.0);
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                bool too_short = false;
+                rc = run_pipelined(ctx, bases, seq_off, n_seqs, P, slab, overlap, too_short, out);
+                if (rc != S2K_OK || !too_short) return rc;
+                STAGE(700000 + attempt);
+                CU(cudaStreamSynchronize(ctx->s_h2d)); CU(cudaStreamSynchronize(ctx->s_d2h)); CU(cudaStreamSynchronize(st));
+                overlap = std::min<uint64_t>(n_bases, overlap * 8);
+            }                                              // still not enough: the whole batch at once, below
+        }
     }
     if ((rc = ensure(ctx, ctx->d_bases, n_bases + 16, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_seq_off, (n_seqs + 1) * 8, false))) return rc;

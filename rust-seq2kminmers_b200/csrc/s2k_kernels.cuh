@@ -1236,6 +1236,44 @@ __global__ void k_add_seq(uint4 *__restrict__ mins, uint64_t n, uint32_t add)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mins[i].w += add;
 }
 
+// ---- one long sequence travelling through s2k_run in pieces (run_pipelined): bookkeeping kernels.
+// A piece is the owned range [b0, b1) of the sequence plus a right overlap, processed as a sequence of its own.
+// k_piece_cut: i1 = minimizers whose start lies in the owned range (all of them for the last piece), n_keep =
+// minimizers left after the AVX-512 tail rule (last piece only: those ending at or beyond e16 are dropped).
+__global__ void k_piece_cut(const uint4 *__restrict__ mins, uint64_t n_min, uint32_t own_len, uint32_t e16,
+                            unsigned long long *__restrict__ out)
+{
+    uint64_t lo = 0, hi = n_min;                 // first minimizer with start >= own_len
+    while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (mins[mid].y < own_len) lo = mid + 1; else hi = mid; }
+    out[0] = lo;
+    lo = 0; hi = n_min;                          // first minimizer with end >= e16
+    while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (mins[mid].z < e16) lo = mid + 1; else hi = mid; }
+    out[1] = lo;
+}
+// kept (HPC) bases among b[0, n): b[i] != b[i-1], b[0] counts (pieces are cut at run boundaries)
+__global__ void __launch_bounds__(256) k_count_kept(const uint8_t *__restrict__ b, uint64_t n, unsigned long long *__restrict__ acc)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += (i == 0 || b[i] != b[i - 1]) ? 1u : 0u;
+    c = warp_sum64(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(acc, c);
+}
+__global__ void k_piece_shift_items(uint32_t *__restrict__ start, uint32_t *__restrict__ end, uint64_t n, uint32_t add)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { start[i] += add; end[i] += add; }
+}
+__global__ void k_piece_shift_mins(uint4 *__restrict__ mins, uint64_t n, uint32_t add, uint32_t seq)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint4 m = mins[i];
+        m.y += add; m.z += add; m.w = seq;
+        mins[i] = m;
+    }
+}
+
 // 2-bit transport (s2k_run): the host packs ACGT-only slabs 4 bases per byte (base i in bits 2*(i%4), code = (b>>1)&3:
 // A0 C1 T2 G3) to quarter the PCIe traffic; this kernel restores the ASCII bytes the rest of the path works on.
 __global__ void __launch_bounds__(256) k_unpack2(const uint32_t *__restrict__ packed, uint64_t n_bases, uint8_t *__restrict__ out)

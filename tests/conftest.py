@@ -1,3 +1,4 @@
+import os
 import importlib
 import subprocess
 import sys
@@ -9,6 +10,9 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+
+
+os.environ.setdefault("S2K_WATCHDOG", "1")      # the library reports where a pipelined run stands every 5 s once it takes that long
 
 
 def pytest_configure(config):

@@ -79,6 +79,38 @@ def test_pipelined_host_path_emulated(S, O, emu_ctx, batches):
         emu_ctx.set_transport(0, 0.7)
 
 
+def _norun(rng, n):
+    """Random ACGT without equal neighbours: the HPC length equals the raw length."""
+    import numpy as np
+    steps = rng.integers(1, 4, n)
+    steps[0] = rng.integers(0, 4)
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[np.cumsum(steps) % 4].copy()
+
+
+def test_long_sequences_travel_in_pieces_emulated(S, O, emu_ctx, batches):
+    """A sequence longer than 1.5 slabs is cut into pieces with a right overlap (run_pipelined): owned minimizers and
+    windows, coordinates of the whole sequence, and the AVX-512 tail rule applied by the last piece (lengths chosen so
+    that it fires: S = kept - l + 1 is a multiple of 16)."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    l, k, d = 21, 3, 0.3
+    fire = 16 * 1200 + l - 1                               # S % 16 == 0 when every base is kept
+    seqs = [batches.seq(150), batches.seq(25000, runp=0.4), _norun(rng, fire), batches.seq(0), _norun(rng, fire + 5),
+            batches.seq(20000, alphabet=b"ACGTN"), batches.seq(fire),                     # Simd: the raw length decides
+            np.concatenate([batches.seq(15000), np.full(3000, 65, np.uint8)])]            # ends in a long homopolymer
+    bases, so = batches.pack(seqs)
+    emu_ctx.set_slab_bytes(8000)
+    try:
+        for mode, var, ratio in ((S.HashMode.HpcSimd, 0, 0.7), (S.HashMode.Simd, 0, 0.0), (S.HashMode.Hpc, 0, 0.0),
+                                 (S.HashMode.Regular, 0, 0.7), (S.HashMode.HpcSimd, 1, 0.0)):
+            emu_ctx.set_transport(3, ratio)
+            got = emu_ctx.run(bases, so, l, k, d, mode, S.HashVariant(var), want_minimizers=True)
+            assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
+    finally:
+        emu_ctx.set_slab_bytes(0)
+        emu_ctx.set_transport(0, 0.7)
+
+
 def test_random_parameter_fuzz_emulated(S, O, emu_ctx, batches):
     for bases, so, (l, k, d, mode, var) in fuzz_cases(batches, 25, 40000):
         got = emu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)

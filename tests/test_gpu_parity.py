@@ -177,6 +177,34 @@ def test_pipelined_host_path(S, O, gpu_ctx, batches):
         gpu_ctx.set_transport(0, 0.7)
 
 
+def test_long_sequences_travel_in_pieces(S, O, gpu_ctx, batches):
+    """s2k_run cuts sequences longer than 1.5 slabs into pieces with a right overlap; results == one-shot run == oracle.
+    Lengths are chosen so that the AVX-512 tail rule fires (S = kept - l + 1 multiple of 16) and does not fire."""
+    rng = np.random.default_rng(5)
+
+    def norun(n):
+        steps = rng.integers(1, 4, n)
+        steps[0] = rng.integers(0, 4)
+        return np.frombuffer(b"ACGT", dtype=np.uint8)[np.cumsum(steps) % 4].copy()
+
+    l, k, d = 31, 5, 0.05
+    fire = 16 * 40000 + l - 1
+    seqs = [batches.seq(150), batches.seq(900000, runp=0.4), norun(fire), batches.seq(0), norun(fire + 3),
+            batches.seq(700000, alphabet=b"ACGTN"), batches.seq(fire), batches.seq(5000),
+            np.concatenate([batches.seq(500000), np.full(70000, 84, np.uint8)])]
+    bases, so = batches.pack(seqs)
+    gpu_ctx.set_slab_bytes(100000)
+    try:
+        for mode, var, ratio in ((S.HashMode.HpcSimd, 0, 0.7), (S.HashMode.Simd, 0, 0.0), (S.HashMode.Hpc, 0, 0.5),
+                                 (S.HashMode.Regular, 0, 0.7), (S.HashMode.HpcSimd, 1, 0.0)):
+            gpu_ctx.set_transport(0, ratio)
+            got = gpu_ctx.run(bases, so, l, k, d, mode, S.HashVariant(var), want_minimizers=True)
+            assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
+    finally:
+        gpu_ctx.set_slab_bytes(0)
+        gpu_ctx.set_transport(0, 0.7)
+
+
 def test_one_sequence_split_across_ranks(S, O, gpu_ctx):
     """SURVEY 8(e), config 4 shape: a 30-Mbp sequence processed as 4 base ranges (overlap-and-trim by ownership) gives
     exactly the k-min-mers of the whole sequence, for the 31-bit hash, the scalar HPC profile and ntHash1 HpcSimd
