@@ -129,8 +129,10 @@ int  s2k_ctx_set_flags(s2k_ctx *ctx, uint32_t flags);
 int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs,
             const s2k_params *params, s2k_result *out);
 
-/* Large host batches are streamed through the device in slabs cut at sequence boundaries (H2D, kernels and D2H
- * overlap on three streams).  bytes = target slab size (0 = default 256 MiB); batches up to 1.5 slabs go in one piece. */
+/* Large host batches are streamed through the device in slabs (H2D, kernels and D2H overlap on three streams): runs of
+ * whole sequences, and pieces of any sequence longer than 1.5 slabs (a chromosome) -- a piece owns a base range and
+ * carries a right overlap that completes its last windows; results are identical to a one-shot run.
+ * bytes = target slab size (0 = default 256 MiB); batches up to 1.5 slabs go in one piece. */
 int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes);
 
 /* Host ingest + run: the loop of the reference's driver, `parallel_fastx(&filename, nb_threads, task)` with
