@@ -811,13 +811,13 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             ++r0;
             continue;
         }
-        uint64_t r1 = r0, nb = 0;
-        while (r1 < n_seqs) {
-            const uint64_t len = seq_off[r1 + 1] - seq_off[r1];
-            if (len > slab_bytes + slab_bytes / 2 && len > (uint64_t)P.l) break;            // a long one: pieces
-            if (r1 > r0 && nb + len > slab_bytes) break;
-            nb += len; ++r1;
-        }
+        // whole sequences up to one slab of bases (binary search: batches of 10^8 short reads are common); a sequence
+        // between 1 and 1.5 slabs travels alone, anything longer is met as r0 on a later round and goes in pieces
+        const uint64_t *e = std::upper_bound(seq_off + r0 + 1, seq_off + n_seqs + 1, seq_off[r0] + slab_bytes);
+        uint64_t r1 = (uint64_t)(e - seq_off) - 1;
+        if (r1 <= r0) r1 = r0 + 1;
+        if (r1 > n_seqs) r1 = n_seqs;
+        const uint64_t nb = seq_off[r1] - seq_off[r0];
         slabs.push_back(Slab{r0, r1, false, false, false, seq_off[r0], seq_off[r1], seq_off[r1]});
         max_b = std::max(max_b, nb);
         max_n = std::max(max_n, r1 - r0);
