@@ -1,5 +1,5 @@
 // cuda_emu.h -- TEST-ONLY shim that lets the product's CUDA sources (s2k_kernels.cuh, s2k_api.cu) be
-// compiled by g++ and executed on host threads, one std::thread per CUDA thread, with real barriers for
+// compiled by g++ and executed on the host, one fiber (or std::thread, see below) per CUDA thread, with barriers for
 // __syncthreads and lock-step warp collectives.  It exists so that the kernel LOGIC (tile stitching, halos,
 // look-back, tail rules, edge cases) can be checked against the oracle in the CPU-only test tier, where no
 // GPU is available.  It is never part of the product: rust-seq2kminmers_b200 loads libs2k_b200.so (nvcc,
@@ -34,16 +34,110 @@ struct alignas(16) ulonglong2 { unsigned long long x, y; };
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 
+// Two execution models.  Default: FIBERS -- every emulated CUDA thread is a ucontext fiber, the fibers of a CTA share
+// one OS thread (CTAs of a concurrent launch get one OS thread each) and switch at barriers and warp collectives.
+// Hundreds of OS threads meeting at futex barriers cost minutes of system time per test on a small VM; fibers switch
+// in user space.  Under AddressSanitizer (tests/test_emu_asan.py), or with -DS2K_EMU_THREADS, every CUDA thread is a
+// real std::thread instead (ASan does not follow swapcontext without annotations).
+#if !defined(__SANITIZE_ADDRESS__) && !defined(S2K_EMU_THREADS)
+#define S2K_EMU_FIBERS 1
+#include <ucontext.h>
+#endif
+
 namespace emu {
+#ifdef S2K_EMU_FIBERS
+struct Bar { unsigned n = 0, count = 0, gen = 0; };
+struct Block {
+    Bar bar;
+    std::vector<Bar> wbar;
+    std::vector<uint64_t> slot;      // 32 per warp
+    uint8_t *smem = nullptr;
+    ucontext_t sched;
+    std::vector<ucontext_t> ctx;
+    std::vector<char *> stacks;
+    std::vector<char> done;
+    unsigned cur = 0;
+    const std::function<void()> *body = nullptr;
+};
+#else
 struct Block {
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<std::barrier<>>> wbar;
     std::vector<uint64_t> slot;      // 32 per warp
     uint8_t *smem = nullptr;
 };
+#endif
 inline thread_local Block *blk = nullptr;
 inline thread_local emu_dim3 tIdx, bIdx, bDim, gDim;
 
+#ifdef S2K_EMU_FIBERS
+inline void fiber_yield() { Block *B = blk; swapcontext(&B->ctx[B->cur], &B->sched); }
+inline void bar_wait(Bar &x)
+{
+    const unsigned g = x.gen;
+    if (++x.count == x.n) { x.count = 0; ++x.gen; }
+    else while (x.gen == g) fiber_yield();
+}
+inline void block_barrier() { bar_wait(blk->bar); }
+inline void warp_barrier(unsigned w) { bar_wait(blk->wbar[w]); }
+inline void fiber_entry()
+{
+    Block *B = blk;
+    (*B->body)();
+    B = blk;
+    B->done[B->cur] = 1;
+    swapcontext(&B->ctx[B->cur], &B->sched);
+}
+constexpr size_t FIBER_STACK = 256 * 1024;
+// runs one CTA to completion on the calling OS thread
+inline void run_block(unsigned b, unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()> &body)
+{
+    Block B;
+    const unsigned nw = (block + 31) / 32;
+    B.bar.n = block;
+    B.wbar.resize(nw);
+    for (unsigned w = 0; w < nw; ++w) B.wbar[w].n = std::min(32u, block - 32 * w);
+    B.slot.assign((size_t)nw * 32, 0);
+    B.smem = smem_bytes ? (uint8_t *)aligned_alloc(128, (smem_bytes + 127) & ~size_t(127)) : nullptr;
+    B.ctx.resize(block); B.stacks.resize(block); B.done.assign(block, 0); B.body = &body;
+    blk = &B; bIdx.x = b; bDim.x = block; gDim.x = grid;
+    for (unsigned t = 0; t < block; ++t) {
+        B.stacks[t] = (char *)malloc(FIBER_STACK);
+        getcontext(&B.ctx[t]);
+        B.ctx[t].uc_stack.ss_sp = B.stacks[t];
+        B.ctx[t].uc_stack.ss_size = FIBER_STACK;
+        B.ctx[t].uc_link = &B.sched;
+        makecontext(&B.ctx[t], fiber_entry, 0);
+    }
+    for (unsigned remaining = block; remaining;)
+        for (unsigned t = 0; t < block; ++t)
+            if (!B.done[t]) {
+                B.cur = t; tIdx.x = t;
+                swapcontext(&B.sched, &B.ctx[t]);
+                if (B.done[t]) --remaining;
+            }
+    for (char *st : B.stacks) free(st);
+    free(B.smem);
+    blk = nullptr;
+}
+// Runs `body` once per emulated CUDA thread.  concurrent=false runs the blocks one after the other (needed for
+// kernels that keep static __shared__ state, which the shim maps to plain statics).
+inline void launch(unsigned grid, unsigned block, size_t smem_bytes, bool concurrent, const std::function<void()> &body)
+{
+    if (concurrent && grid > 1) {
+        std::vector<std::thread> threads;
+        for (unsigned b = 0; b < grid; ++b) threads.emplace_back([&, b]() { run_block(b, grid, block, smem_bytes, body); });
+        for (auto &t : threads) t.join();
+    } else {
+        Block *outer = blk;
+        for (unsigned b = 0; b < grid; ++b) run_block(b, grid, block, smem_bytes, body);
+        blk = outer;
+    }
+}
+#else
+inline void block_barrier() { blk->bar->arrive_and_wait(); }
+inline void warp_barrier(unsigned w) { blk->wbar[w]->arrive_and_wait(); }
+inline void fiber_yield() { sched_yield(); }
 // Runs `body` once per emulated CUDA thread.  concurrent=false runs the blocks one after the other (needed for
 // kernels that keep static __shared__ state, which the shim maps to plain statics).
 inline void launch(unsigned grid, unsigned block, size_t smem_bytes, bool concurrent, const std::function<void()> &body)
@@ -78,6 +172,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, bool concur
         }
     }
 }
+#endif
 } // namespace emu
 
 #define threadIdx emu::tIdx
@@ -85,7 +180,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, bool concur
 #define blockDim emu::bDim
 #define gridDim emu::gDim
 
-static inline void __syncthreads() { emu::blk->bar->arrive_and_wait(); }
+static inline void __syncthreads() { emu::block_barrier(); }
 
 template <typename T> static inline T emu_warp_exchange(T v, int src_lane_or_neg, bool take)
 {
@@ -93,13 +188,13 @@ template <typename T> static inline T emu_warp_exchange(T v, int src_lane_or_neg
     uint64_t bits = 0;
     std::memcpy(&bits, &v, sizeof(T));
     emu::blk->slot[w * 32 + lane] = bits;
-    emu::blk->wbar[w]->arrive_and_wait();
+    emu::warp_barrier(w);
     T r = v;
     if (take && src_lane_or_neg >= 0 && src_lane_or_neg < 32) {
         uint64_t o = emu::blk->slot[w * 32 + (unsigned)src_lane_or_neg];
         std::memcpy(&r, &o, sizeof(T));
     }
-    emu::blk->wbar[w]->arrive_and_wait();
+    emu::warp_barrier(w);
     return r;
 }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int o)
@@ -121,16 +216,16 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int src)
 {
     return emu_warp_exchange(v, src & 31, true);
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::blk->wbar[threadIdx.x >> 5]->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(threadIdx.x >> 5); }
 static inline unsigned __ballot_sync(unsigned, bool pred)
 {
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     emu::blk->slot[w * 32 + lane] = pred ? 1 : 0;
-    emu::blk->wbar[w]->arrive_and_wait();
+    emu::warp_barrier(w);
     unsigned r = 0;
     const unsigned n = std::min(32u, blockDim.x - 32 * w);
     for (unsigned i = 0; i < n; ++i) r |= (unsigned)emu::blk->slot[w * 32 + i] << i;
-    emu::blk->wbar[w]->arrive_and_wait();
+    emu::warp_barrier(w);
     return r;
 }
 static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
@@ -168,7 +263,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
     }
     return r;
 }
-static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline void __nanosleep(unsigned) { sched_yield(); }     // spin-waits are on other CTAs (own OS threads)
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

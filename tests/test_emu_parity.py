@@ -95,14 +95,14 @@ def test_long_sequences_travel_in_pieces_emulated(S, O, emu_ctx, batches):
     rng = np.random.default_rng(77)
     l, k, d = 21, 3, 0.3
     fire = 16 * 700 + l - 1                                # S % 16 == 0 when every base is kept
-    seqs = [batches.seq(150), _norun(rng, fire), batches.seq(0),
+    seqs = [batches.seq(150), batches.seq(14000, runp=0.4), _norun(rng, fire), batches.seq(0), _norun(rng, fire + 5),
             batches.seq(12000, alphabet=b"ACGTN"), batches.seq(fire),                     # Simd: the raw length decides
             np.concatenate([batches.seq(8000), np.full(3500, 65, np.uint8)])]             # ends in a long homopolymer
     bases, so = batches.pack(seqs)
     emu_ctx.set_slab_bytes(6000)
     try:
-        for mode, var, ratio in ((S.HashMode.HpcSimd, 0, 0.7), (S.HashMode.Simd, 0, 0.0), (S.HashMode.Hpc, 0, 0.7)):
-            # (the GPU tier adds Regular, the 31-bit hash and larger sizes)
+        for mode, var, ratio in ((S.HashMode.HpcSimd, 0, 0.7), (S.HashMode.Simd, 0, 0.0), (S.HashMode.Hpc, 0, 0.7),
+                                 (S.HashMode.Regular, 0, 0.7), (S.HashMode.HpcSimd, 1, 0.0)):
             emu_ctx.set_transport(3, ratio)
             got = emu_ctx.run(bases, so, l, k, d, mode, S.HashVariant(var), want_minimizers=True)
             assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
