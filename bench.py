@@ -259,11 +259,11 @@ def main():
     k_ms = float(np.mean(kms))
     peak, peak_src = peaks()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    # DRAM traffic of the kernel from the committed `ncu --set full` capture (profiles/r2f_kernel_summary.txt:
+    # DRAM traffic of the kernel from the committed `ncu --set full` capture (profiles/r1_final_kernel_summary.txt:
     # 1.1087 GB read + 0.3217 GB written for a 1.000 Gbp launch of this workload shape), scaled to this launch.
     traffic = (1.1087e9 + 0.3217e9) * (n_bases / 1e9) if args.workload == "c2" and mode == 3 and variant == 0 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r2f_kernel_summary.txt, scaled by bases" if traffic else None,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_final_kernel_summary.txt, scaled by bases" if traffic else None,
                 "algorithmic_bytes": alg_bytes,
                 "kernel": "k_minimizers", "launches_per_step": kl, "ms_per_step_in_kernel": k_ms,
                 "window_stage_ms": float(np.mean(wms)), "bytes_per_base": alg_bytes / n_bases, "peak_source": peak_src}
