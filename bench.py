@@ -267,6 +267,17 @@ def main():
                 "algorithmic_bytes": alg_bytes,
                 "kernel": "k_minimizers", "launches_per_step": kl, "ms_per_step_in_kernel": k_ms,
                 "window_stage_ms": float(np.mean(wms)), "bytes_per_base": alg_bytes / n_bases, "peak_source": peak_src}
+    if traffic:
+        # What actually bounds the kernel (context for the HBM fraction above): instruction
+        # throughput.  35.3 thread-instructions per base, 52 % of them on the ALU pipe (16 lanes per SM sub-partition),
+        # from the committed ncu capture; ceilings from the SM count and the sampled clock.
+        mhz = float(clocks.get("sm_mhz") or 1965.0) if isinstance(clocks, dict) else 1965.0
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms * 4 * 32 * mhz * 1e6            # thread-instructions per second
+        ipb, alu_share = 35.3, 0.52
+        rate = n_bases / (k_ms * 1e-3)
+        roofline["instruction_bound"] = {"thread_instr_per_base": ipb, "source": "profiles/r1_final_kernel_summary.txt",
+                                         "issue_frac": rate * ipb / issue_peak, "alu_pipe_frac": rate * ipb * alu_share / (issue_peak / 2)}
 
     # ------------------------------------------------------------------ end to end through s2k_run (host buffers)
     e2e = None
