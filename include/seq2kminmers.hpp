@@ -58,6 +58,18 @@ class Context {
         check(s2k_run(ctx_, bases, seq_off, n_seqs, &p, &r));
         return r;
     }
+    // The driver's file mode (src/main.rs:50-81): FASTA/FASTQ file -> k-min-mers of every record, nb_threads parser threads.
+    s2k_result run_fastx(const std::string &path, int nb_threads, size_t l, size_t k, double density, HashMode mode,
+                         HashVariant variant = HashVariant::NT1_32)
+    {
+        s2k_params p{(uint32_t)l, (uint32_t)k, density, (int32_t)mode, (int32_t)variant};
+        s2k_result r;
+        check(s2k_run_fastx(ctx_, path.c_str(), nb_threads, &p, &r));
+        return r;
+    }
+    // Host-side knobs of run(): slab size of the three-stream pipeline, share of slabs packed to 2 bits/base.
+    void set_slab_bytes(uint64_t bytes) { check(s2k_ctx_set_slab_bytes(ctx_, bytes)); }
+    void set_transport(int host_threads, double pack_ratio) { check(s2k_ctx_set_transport(ctx_, host_threads, pack_ratio)); }
     s2k_rle_result encode_rle(const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs)
     {
         s2k_rle_result r;

@@ -59,9 +59,15 @@ constexpr int CAP   = HT * CH;      // owners hashed per pass (a second pass cov
 static_assert(CH % 4 == 0 && ((CH / 4) & 1) == 1 && CH <= 128 && HT <= NT && 2 * CAP >= WIN, "hash geometry");
 constexpr int XB    = 256;          // capacity of the left context, in kept (HPC) bases
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
-constexpr int HL    = 1024;         // hit-list entries emitted per round
+#ifndef S2K_HL
+#define S2K_HL 1024
+#endif
+constexpr int HL    = S2K_HL;         // hit-list entries emitted per round
 constexpr int DIRTY_MAX = 62;
-constexpr int SOC   = 128;          // sequence offsets cached per tile (tiles with more starts search global memory)
+#ifndef S2K_SOC
+#define S2K_SOC 128
+#endif
+constexpr int SOC   = S2K_SOC;          // sequence offsets cached per tile (tiles with more starts search global memory)
 // Base classes are stored pre-scaled by 8 (the size of a table entry): code(A,C,G,T) = 0,8,16,24 and the two rare
 // classes (seed 0 / seed 1) = 32,40.  Three tables of (forward, reverse) 32-bit pairs:
 //   xy  general: entry (out,in) at byte 8*code(out)+code(in) -- collision-free for all 6x6 combinations
