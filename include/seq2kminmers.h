@@ -143,6 +143,18 @@ int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes);
 int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_params *params, s2k_result *out);
 int s2k_last_fastx(const s2k_ctx *ctx, uint64_t *n_seqs, uint64_t *n_bases, const uint8_t **bases, const uint64_t **seq_off);
 
+/* 2-bit packed input (what the reference's src/old/hpc_2bit.rs:1-16 set out to do).  `packed` holds
+ * the concatenated bases of the batch four per byte: base i in bits 2*(i%4) of byte i/4, code (ascii >> 1) & 3, i.e.
+ * A=0 C=1 T=2 G=3; sequences follow each other without padding and seq_off counts BASES, as in s2k_run.  Only
+ * upper-case A/C/G/T can be expressed -- input on which the ASCII form gives the same results in every mode.  A quarter
+ * of the bytes cross PCIe and no host thread packs; everything else (slabs, pieces of long sequences, results) is
+ * s2k_run.
+ * s2k_pack2 is the matching helper: packs n_bases ASCII bases on host_threads threads; returns 0, or 1 if some byte was
+ * not upper-case A/C/G/T (the output is then unusable), -1 on null arguments. */
+int s2k_run_packed2(s2k_ctx *ctx, const uint8_t *packed, const uint64_t *seq_off, uint64_t n_seqs,
+                    const s2k_params *params, s2k_result *out);
+int64_t s2k_pack2(const uint8_t *bases, uint64_t n_bases, uint8_t *packed_out, int host_threads);
+
 /* Transport of large host batches (s2k_run, s2k_run_fastx).  PCIe, not the GPU, bounds the end-to-end rate, so a share
  * `pack_ratio` of the slabs (default 0.7; 0 = never) is packed to 2 bits per base by `host_threads` host threads
  * (default 0 = 3/4 of the hardware threads, at most 16; AVX-512) into pinned staging, copied and unpacked on the device, while the

@@ -58,6 +58,15 @@ class Context {
         check(s2k_run(ctx_, bases, seq_off, n_seqs, &p, &r));
         return r;
     }
+    // 2-bit packed input (4 bases per byte, A0 C1 T2 G3; seq_off counts bases): a quarter of the PCIe bytes, no host packing.
+    s2k_result run_packed2(const uint8_t *packed, const uint64_t *seq_off, uint64_t n_seqs, size_t l, size_t k, double density,
+                           HashMode mode, HashVariant variant = HashVariant::NT1_32)
+    {
+        s2k_params p{(uint32_t)l, (uint32_t)k, density, (int32_t)mode, (int32_t)variant};
+        s2k_result r;
+        check(s2k_run_packed2(ctx_, packed, seq_off, n_seqs, &p, &r));
+        return r;
+    }
     // The driver's file mode (src/main.rs:50-81): FASTA/FASTQ file -> k-min-mers of every record, nb_threads parser threads.
     s2k_result run_fastx(const std::string &path, int nb_threads, size_t l, size_t k, double density, HashMode mode,
                          HashVariant variant = HashVariant::NT1_32)

@@ -82,7 +82,7 @@ ABI_SYMBOLS = (
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
     "s2k_ctx_set_slab_bytes", "s2k_last_kernel_kind", "s2k_run_fastx", "s2k_last_fastx", "s2k_ctx_set_transport",
-    "s2k_last_transport",
+    "s2k_last_transport", "s2k_run_packed2", "s2k_pack2",
 )
 
 
@@ -127,6 +127,10 @@ class Library:
         L.s2k_ctx_set_timing.argtypes = [vp, C.c_int]
         L.s2k_ctx_set_slab_bytes.restype = C.c_int
         L.s2k_ctx_set_slab_bytes.argtypes = [vp, C.c_uint64]
+        L.s2k_run_packed2.restype = C.c_int
+        L.s2k_run_packed2.argtypes = L.s2k_run.argtypes
+        L.s2k_pack2.restype = C.c_int64
+        L.s2k_pack2.argtypes = [vp, C.c_uint64, vp, C.c_int]
         L.s2k_last_transport.restype = C.c_int
         L.s2k_last_transport.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.s2k_ctx_set_transport.restype = C.c_int
@@ -271,20 +275,23 @@ class Context:
     # -- host buffers in, host (pinned) results out ------------------------------------------------------
     def run(self, bases, seq_off, l: int, k: int, density: float, mode: HashMode,
             variant: HashVariant = HashVariant.NT1_32, want_minimizers: bool = False, copy: bool = True,
-            no_tail_rule: bool = False, general_kernel: bool = False, debug_tiny_cap: bool = False) -> KminmersBatch:
+            no_tail_rule: bool = False, general_kernel: bool = False, debug_tiny_cap: bool = False,
+            packed2: bool = False) -> KminmersBatch:
+        """packed2=True: `bases` is 2-bit packed input (see pack2 / s2k_run_packed2), seq_off still counts bases."""
         b = _as_u8(bases)
         so = np.ascontiguousarray(seq_off, dtype=np.uint64)
         if so.ndim != 1 or so.shape[0] < 1:
             raise ValueError("seq_off must hold n_seqs+1 offsets")
         n = so.shape[0] - 1
-        if int(so[-1]) > b.shape[0]:
+        if (int(so[-1]) + 3) // 4 > b.shape[0] if packed2 else int(so[-1]) > b.shape[0]:
             raise ValueError("seq_off[-1] exceeds len(bases)")
         self._check(self.lib.c.s2k_ctx_set_flags(self.h, (1 if want_minimizers else 0) | (2 if no_tail_rule else 0) |
                                                  (4 if general_kernel else 0) | (8 if debug_tiny_cap else 0)))
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
         try:
-            self._check(self.lib.c.s2k_run(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(p), C.byref(r)))
+            fn = self.lib.c.s2k_run_packed2 if packed2 else self.lib.c.s2k_run
+            self._check(fn(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(p), C.byref(r)))
         finally:
             self.lib.c.s2k_ctx_set_flags(self.h, 0)
         f = (lambda a: a.copy()) if copy else (lambda a: a)
@@ -293,6 +300,15 @@ class Context:
                              f(_view(r.end, r.n_items, np.uint32)), f(_view(r.rev, r.n_items, np.uint8)),
                              f(_view(r.km_off, n + 1, np.uint64)), f(_view(r.min_off, n + 1, np.uint64)),
                              f(_view(r.min_cnt, n, np.uint32)), int(r.n_minimizers), mins)
+
+    def pack2(self, bases, host_threads: int = 8):
+        """ASCII A/C/G/T -> 2-bit packed bytes for run(..., packed2=True) (s2k_pack2).  Raises on any other byte."""
+        b = _as_u8(bases)
+        out = np.zeros((b.shape[0] + 3) // 4 + 8, dtype=np.uint8)
+        st = self.lib.c.s2k_pack2(b.ctypes.data, b.shape[0], out.ctypes.data, int(host_threads))
+        if st != 0:
+            raise ValueError("pack2: input holds bytes other than upper-case A/C/G/T")
+        return out
 
     # -- device buffers in, device results out ------------------------------------------------------------
     def run_device(self, d_bases_ptr: int, d_seq_off_ptr: int, n_seqs: int, n_bases: int, l: int, k: int,

@@ -217,9 +217,11 @@ uint64_t pack2_range(const uint8_t *src, uint8_t *dst, size_t lo, size_t hi)   /
     uint64_t bad = 0;
     size_t i = lo;
 #if defined(__x86_64__)
-    const size_t body = (hi - lo) & ~size_t(63);
-    bad += pack2_avx512(src + lo, dst + (lo >> 2), body);
-    i = lo + body;
+    if (host_has_avx512()) {
+        const size_t body = (hi - lo) & ~size_t(63);
+        bad += pack2_avx512(src + lo, dst + (lo >> 2), body);
+        i = lo + body;
+    }
 #endif
     for (; i < hi; i += 4) {
         uint8_t o = 0;
@@ -768,10 +770,15 @@ struct Slab {
     bool piece, first, last;      // piece of sequence r0; first / last piece of it
     uint64_t b0, b1, hi;          // absolute offsets into `bases`: first base copied, end of the owned range, end of the copy
 };
+// packed_in: `bases` is the caller's 2-bit packed batch (s2k_run_packed2) -- slabs are copied as they are and unpacked
+// on the device; the host packers stay idle.
 static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const Plan &P,
-                         uint64_t slab_bytes, uint64_t overlap, bool &overlap_short, s2k_result *out)
+                         uint64_t slab_bytes, uint64_t overlap, bool &overlap_short, s2k_result *out, bool packed_in)
 {
     int rc;
+    auto base_at = [&](uint64_t i) -> uint8_t {             // equality of bases is all the host ever asks
+        return packed_in ? (uint8_t)((bases[i >> 2] >> (2 * (i & 3))) & 3u) : bases[i];
+    };
     overlap_short = false;
     stage_watchdog();
     STAGE(1);
@@ -800,7 +807,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             while (b0 < s1) {
                 uint64_t b1 = std::min(s1, b0 + std::min<uint64_t>(slab_bytes, 1ull << 31));
                 if (s1 - b1 < slab_bytes / 2) b1 = s1;                          // no tiny last piece
-                if (P.hpc) while (b1 < s1 && bases[b1] == bases[b1 - 1]) ++b1;  // cut on a run boundary
+                if (P.hpc) while (b1 < s1 && base_at(b1) == base_at(b1 - 1)) ++b1;  // cut on a run boundary
                 const uint64_t hi = b1 == s1 ? s1 : std::min(s1, b1 + overlap);
                 slabs.push_back(Slab{r0, r0 + 1, true, b0 == s0, b1 == s1, b0, b1, hi});
                 max_b = std::max(max_b, hi - b0);
@@ -841,7 +848,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     // buffers), copied (a quarter of the bytes) and unpacked on the device; the other slabs go as plain ASCII so that
     // PCIe and the packers work at the same time.  A slab with any byte outside upper-case ACGT goes as ASCII.
     int T = ctx->host_threads > 0 ? ctx->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() * 3 / 4));
-    const bool can_pack = host_has_avx512() && ctx->pack_ratio > 0.0 && n_slabs >= 3;
+    const bool can_pack = !packed_in && host_has_avx512() && ctx->pack_ratio > 0.0 && n_slabs >= 3;
     std::vector<int> ps_of(n_slabs, -1);
     std::vector<size_t> packed_slabs;
     if (can_pack) {
@@ -856,6 +863,8 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
         for (int i = 0; i < 2; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
         for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->h_pack[i], max_b / 4 + 64, true))) return rc;
     }
+    if (packed_in)
+        for (int i = 0; i < 2; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
     std::vector<std::atomic<uint32_t>> pk_done(np);
     std::vector<std::atomic<uint64_t>> pk_bad(np);
     for (size_t i = 0; i < np; ++i) { pk_done[i].store(0); pk_bad[i].store(0); }
@@ -909,13 +918,20 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
         STAGE(200000 + (long)s);
         CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_free[b], 0));          // the kernels of slab s-2 are done with it
         ctx->tr_h2d_bytes += (packed ? (nb + 3) / 4 : nb) + (r1 - r0 + 1) * 8;
-        if (packed) ++ctx->tr_packed; else ++ctx->tr_plain;
-        if (packed) {
+        if (packed || packed_in) ++ctx->tr_packed; else ++ctx->tr_plain;
+        if (packed_in) {                                                  // the caller's packed bytes, whatever base the slab starts on
+            const uint64_t by0 = L.b0 >> 2, nby = ((L.hi + 3) >> 2) - by0;
+            ctx->tr_h2d_bytes -= nb; ctx->tr_h2d_bytes += nby;
+            if (nby) CU(cudaMemcpyAsync(ctx->d_pack[b].p, bases + by0, nby, cudaMemcpyHostToDevice, ctx->s_h2d));
+            const int g = (int)std::min<uint64_t>((nb / 16 + 256) / 256, (uint64_t)ctx->sm_count * 8);
+            if (nb) S2K_LAUNCH(k_unpack2, g, 256, 0, ctx->s_h2d, false, ptr<uint32_t>(ctx->d_pack[b]), nb, ptr<uint8_t>(ctx->d_in[b]), (uint32_t)(L.b0 & 3));
+            ctx->launches += 1;
+        } else if (packed) {
             CU(cudaMemcpyAsync(ctx->d_pack[b].p, ctx->h_pack[ps % 3].p, (nb + 3) / 4, cudaMemcpyHostToDevice, ctx->s_h2d));
             CU(cudaEventRecord(ctx->ev_pack[ps % 3], ctx->s_h2d));
             pk_state[ps] = 1;
             const int g = (int)std::min<uint64_t>((nb / 16 + 256) / 256, (uint64_t)ctx->sm_count * 8);
-            S2K_LAUNCH(k_unpack2, g, 256, 0, ctx->s_h2d, false, ptr<uint32_t>(ctx->d_pack[b]), nb, ptr<uint8_t>(ctx->d_in[b]));
+            S2K_LAUNCH(k_unpack2, g, 256, 0, ctx->s_h2d, false, ptr<uint32_t>(ctx->d_pack[b]), nb, ptr<uint8_t>(ctx->d_in[b]), 0u);
             ctx->launches += 1;
         } else {
             if (ps >= 0) pk_state[ps] = 2;
@@ -1003,7 +1019,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
                 rule = S > 16 && S % 16 == 0;
                 if (rule) {                                               // 16th kept base from the end of the sequence
                     uint64_t pos = s1, left = 16;
-                    while (left && pos > s0) { --pos; if (!P.hpc || pos == s0 || bases[pos] != bases[pos - 1]) --left; }
+                    while (left && pos > s0) { --pos; if (!P.hpc || pos == s0 || base_at(pos) != base_at(pos - 1)) --left; }
                     if (pos <= L.b0) { overlap_short = true; return S2K_OK; }   // a homopolymer tail as long as a piece
                     e16 = pos - L.b0;
                 }
@@ -1090,8 +1106,8 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     return S2K_OK;
 }
 
-int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const s2k_params *params,
-            s2k_result *out)
+static int run_host(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const s2k_params *params,
+                    s2k_result *out, bool packed_in)
 {
     if (!ctx) return S2K_ERR_NULL;
     if (!out || !seq_off) return fail(ctx, S2K_ERR_NULL, "null argument");
@@ -1113,7 +1129,7 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
             uint64_t overlap = (uint64_t)std::min(4.0e9, 64.0 * (P.k + 8.0) / frac + 64.0 * P.l + 4096.0);
             for (int attempt = 0; attempt < 3; ++attempt) {
                 bool too_short = false;
-                rc = run_pipelined(ctx, bases, seq_off, n_seqs, P, slab, overlap, too_short, out);
+                rc = run_pipelined(ctx, bases, seq_off, n_seqs, P, slab, overlap, too_short, out, packed_in);
                 if (rc != S2K_OK || !too_short) return rc;
                 STAGE(700000 + attempt);
                 CU(cudaStreamSynchronize(ctx->s_h2d)); CU(cudaStreamSynchronize(ctx->s_d2h)); CU(cudaStreamSynchronize(st));
@@ -1121,11 +1137,21 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
             }                                              // still not enough: the whole batch at once, below
         }
     }
-    if ((rc = ensure(ctx, ctx->d_bases, n_bases + 16, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_bases, n_bases + 32, false))) return rc;
     if ((rc = ensure(ctx, ctx->d_seq_off, (n_seqs + 1) * 8, false))) return rc;
-    if (n_bases) CU(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+    if (packed_in) {
+        const uint64_t nby = (n_bases + 3) / 4;
+        if ((rc = ensure(ctx, ctx->d_pack[0], nby + 64, false))) return rc;
+        if (nby) CU(cudaMemcpyAsync(ctx->d_pack[0].p, bases, nby, cudaMemcpyHostToDevice, st));
+        const int g = (int)std::min<uint64_t>((n_bases / 16 + 256) / 256, (uint64_t)ctx->sm_count * 8);
+        if (n_bases) S2K_LAUNCH(k_unpack2, g, 256, 0, st, false, ptr<uint32_t>(ctx->d_pack[0]), n_bases, ptr<uint8_t>(ctx->d_bases), 0u);
+        ctx->launches += 1;
+        ctx->tr_h2d_bytes = nby + (n_seqs + 1) * 8; ctx->tr_packed = 1; ctx->tr_plain = 0;
+    } else {
+        if (n_bases) CU(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+        ctx->tr_h2d_bytes = n_bases + (n_seqs + 1) * 8; ctx->tr_packed = 0; ctx->tr_plain = 1;
+    }
     CU(cudaMemcpyAsync(ctx->d_seq_off.p, seq_off, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
-    ctx->tr_h2d_bytes = n_bases + (n_seqs + 1) * 8; ctx->tr_packed = 0; ctx->tr_plain = 1;
     s2k_result dev;
     rc = run_device(ctx, ptr<uint8_t>(ctx->d_bases), ptr<uint64_t>(ctx->d_seq_off), n_seqs, n_bases, P, st, &dev);
     if (rc != S2K_OK) return rc;
@@ -1163,6 +1189,36 @@ int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_
     out->min_cnt = ptr<uint32_t>(ctx->h_min_cnt);
     out->minimizers = want_min ? reinterpret_cast<const s2k_minimizer *>(ctx->h_mins.p) : nullptr;
     return S2K_OK;
+}
+
+int s2k_run(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const s2k_params *params,
+            s2k_result *out)
+{
+    return run_host(ctx, bases, seq_off, n_seqs, params, out, false);
+}
+
+int s2k_run_packed2(s2k_ctx *ctx, const uint8_t *packed, const uint64_t *seq_off, uint64_t n_seqs, const s2k_params *params,
+                    s2k_result *out)
+{
+    return run_host(ctx, packed, seq_off, n_seqs, params, out, true);
+}
+
+int64_t s2k_pack2(const uint8_t *bases, uint64_t n_bases, uint8_t *packed_out, int host_threads)
+{
+    if ((!bases || !packed_out) && n_bases) return -1;
+    const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(host_threads, 1), n_bases / (1u << 20) + 1));
+    std::vector<uint64_t> bad((size_t)T, 0);
+    std::vector<std::thread> th;
+    const uint64_t chunk = ((n_bases + T - 1) / T + 63) & ~uint64_t(63);
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+            const uint64_t lo = std::min<uint64_t>(n_bases, chunk * t), hi = std::min<uint64_t>(n_bases, lo + chunk);
+            if (hi > lo) bad[(size_t)t] = pack2_range(bases, packed_out, lo, hi);
+        });
+    for (auto &t : th) t.join();
+    uint64_t total = 0;
+    for (uint64_t b : bad) total += b;
+    return total ? 1 : 0;
 }
 
 int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_params *params, s2k_result *out)

@@ -1282,12 +1282,15 @@ __global__ void k_piece_shift_mins(uint4 *__restrict__ mins, uint64_t n, uint32_
 
 // 2-bit transport (s2k_run): the host packs ACGT-only slabs 4 bases per byte (base i in bits 2*(i%4), code = (b>>1)&3:
 // A0 C1 T2 G3) to quarter the PCIe traffic; this kernel restores the ASCII bytes the rest of the path works on.
-__global__ void __launch_bounds__(256) k_unpack2(const uint32_t *__restrict__ packed, uint64_t n_bases, uint8_t *__restrict__ out)
+// `shift` (0..3): the first base wanted is base `shift` of packed[0] (packed-input batches are cut at arbitrary bases;
+// reads packed[nvec] then, which the callers keep inside their buffers).
+__global__ void __launch_bounds__(256) k_unpack2(const uint32_t *__restrict__ packed, uint64_t n_bases, uint8_t *__restrict__ out,
+                                                 uint32_t shift)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t nvec = (n_bases + 15) / 16;                    // 16 bases = one packed word = one 16-byte store
     for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        const uint32_t pw = packed[v];
+        const uint32_t pw = shift ? __funnelshift_r(packed[v], packed[v + 1], 2 * shift) : packed[v];
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

@@ -111,6 +111,34 @@ def test_long_sequences_travel_in_pieces_emulated(S, O, emu_ctx, batches):
         emu_ctx.set_transport(0, 0.7)
 
 
+def _pack2_numpy(bases):
+    """Independent restatement of the packed layout: base i in bits 2*(i%4) of byte i/4, code (ascii>>1)&3."""
+    import numpy as np
+    c = ((np.asarray(bases, dtype=np.uint8) >> 1) & 3).astype(np.uint8)
+    c = np.concatenate([c, np.zeros((-len(c)) % 4, np.uint8)]).reshape(-1, 4)
+    return (c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)).astype(np.uint8)
+
+
+def test_packed2_input_emulated(S, O, emu_ctx, batches):
+    """s2k_run_packed2 (2-bit packed input) == the oracle on the ASCII form: one-shot, slabs of whole
+    reads and pieces of long sequences (slabs then start at bases that are not multiples of 4)."""
+    import numpy as np
+    seqs = [batches.seq(n) for n in [151, 0, 9001, 33, 20003, 150, 7, 26001, 2]] + [batches.seq(9002, runp=0.5)]
+    bases, so = batches.pack(seqs)
+    packed = emu_ctx.pack2(bases, 3)
+    assert np.array_equal(packed[:(len(bases) + 3) // 4], _pack2_numpy(bases))
+    with pytest.raises(ValueError):
+        emu_ctx.pack2(batches.seq(1000, alphabet=b"ACGTN"))
+    try:
+        for slab in (0, 7000):
+            emu_ctx.set_slab_bytes(slab)
+            for mode, var in ((S.HashMode.HpcSimd, 0), (S.HashMode.Regular, 0), (S.HashMode.Hpc, 0), (S.HashMode.Simd, 1)):
+                got = emu_ctx.run(packed, so, 21, 3, 0.2, mode, S.HashVariant(var), want_minimizers=True, packed2=True)
+                assert_batch_matches_oracle(O, got, bases, so, 21, 3, 0.2, mode, var)
+    finally:
+        emu_ctx.set_slab_bytes(0)
+
+
 def test_random_parameter_fuzz_emulated(S, O, emu_ctx, batches):
     for bases, so, (l, k, d, mode, var) in fuzz_cases(batches, 25, 40000):
         got = emu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)

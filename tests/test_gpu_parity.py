@@ -205,6 +205,24 @@ def test_long_sequences_travel_in_pieces(S, O, gpu_ctx, batches):
         gpu_ctx.set_transport(0, 0.7)
 
 
+def test_packed2_input(S, O, gpu_ctx, batches):
+    """s2k_run_packed2: 2-bit packed host input == the oracle on the ASCII form (one-shot, slabs, pieces)."""
+    seqs = [batches.seq(n) for n in [151, 0, 90001, 33, 400003, 150, 7, 260001, 2]] + [batches.seq(90002, runp=0.5)]
+    bases, so = batches.pack(seqs)
+    packed = gpu_ctx.pack2(bases)
+    c = ((bases >> 1) & 3).astype(np.uint8)
+    c = np.concatenate([c, np.zeros((-len(c)) % 4, np.uint8)]).reshape(-1, 4)
+    assert np.array_equal(packed[:(len(bases) + 3) // 4], c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6))
+    try:
+        for slab in (0, 70000):
+            gpu_ctx.set_slab_bytes(slab)
+            for mode, var in ((S.HashMode.HpcSimd, 0), (S.HashMode.Regular, 0), (S.HashMode.Hpc, 0), (S.HashMode.Simd, 1)):
+                got = gpu_ctx.run(packed, so, 31, 5, 0.05, mode, S.HashVariant(var), want_minimizers=True, packed2=True)
+                assert_batch_matches_oracle(O, got, bases, so, 31, 5, 0.05, mode, var)
+    finally:
+        gpu_ctx.set_slab_bytes(0)
+
+
 def test_one_sequence_split_across_ranks(S, O, gpu_ctx):
     """SURVEY 8(e), config 4 shape: a 30-Mbp sequence processed as 4 base ranges (overlap-and-trim by ownership) gives
     exactly the k-min-mers of the whole sequence, for the 31-bit hash, the scalar HPC profile and ntHash1 HpcSimd
