@@ -101,6 +101,7 @@ struct s2k_ctx {
     uint64_t slab_bytes = 0;        // 0 = default
     Buf d_in[2], d_in_off[2], h_off_stage[2];
     Buf d_piece, h_piece;           // long sequences in pieces: kept-base counter and cut results
+    Buf d_stage;                    // a slab's results parked for the D2H while the next slab is computed
     Buf d_pack[2], h_pack[3];       // 2-bit transport: device landing buffers, ring of pinned staging buffers
     cudaEvent_t ev_pack[3] = {nullptr, nullptr, nullptr};
     int host_threads = 0;           // 0 = 3/4 of the hardware threads, at most 16 (measured best on a 16-core host)
@@ -615,7 +616,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
                   &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in_off[0], &ctx->d_in_off[1],
-                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->d_piece, &ctx->h_piece, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1],
+                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1],
                   &ctx->h_pack[0], &ctx->h_pack[1], &ctx->h_pack[2]};
     for (Buf *b : all) release(*b);
     if (ctx->tm.created) {
@@ -972,7 +973,6 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             if ((rc = issue_h2d(s + 1))) return rc;
         }
         CU(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));                    // inputs of this slab have landed
-        CU(cudaStreamWaitEvent(st, ctx->ev_out, 0));                      // results of the previous slab have left
         s2k_result dev;
         STAGE(300000 + (long)s);
         rc = run_device(ctx, ptr<uint8_t>(ctx->d_in[b]), ptr<uint64_t>(ctx->d_in_off[b]), ns, nb, L.piece ? PP : P, st, &dev);
@@ -1051,7 +1051,6 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             }
         }
         CU(cudaEventRecord(ctx->ev_free[b], st));
-        CU(cudaEventRecord(ctx->ev_done, st));
         // host result buffers: sized from the first slab's rates, grown (rarely) if a later slab is denser
         uint64_t need_i = items + ni, need_m = mins + nm;
         if (s == 0 && nb) {
@@ -1068,22 +1067,47 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             if ((rc = ensure_keep(ctx, ctx->h_rev, std::max<uint64_t>(need_i, 1), items))) return rc;
             if (want_min && (rc = ensure_keep(ctx, ctx->h_mins, std::max<uint64_t>(need_m, 1) * 16, mins * 16))) return rc;
         }
+        // Park the slab's results in a staging buffer (device-to-device, microseconds) and send them home from there:
+        // the kernels of the next slab then overlap this slab's D2H instead of waiting for it.
+        const uint64_t tail = (!L.piece && s + 1 == n_slabs) ? 1 : 0;       // the last slab also brings the final prefix
+        const uint64_t n_off = L.piece ? 0 : ns + tail, n_cnt = L.piece ? 0 : ns;
+        const uint64_t nmw = want_min ? nm : 0;
+        const uint64_t o_hash = 0, o_mins = o_hash + ni * 8, o_km = o_mins + nmw * 16, o_mo = o_km + n_off * 8,
+                       o_start = o_mo + n_off * 8, o_end = o_start + ni * 4, o_cnt = o_end + ni * 4, o_rev = o_cnt + n_cnt * 4,
+                       stage_bytes = o_rev + ni;
+        CU(cudaStreamWaitEvent(st, ctx->ev_out, 0));                      // the previous slab's results have left the staging buffer
+        if (stage_bytes > ctx->d_stage.cap) {
+            CU(cudaStreamSynchronize(ctx->s_d2h));
+            if ((rc = ensure(ctx, ctx->d_stage, stage_bytes + stage_bytes / 4 + 4096, false))) return rc;
+        }
+        uint8_t *sg = ptr<uint8_t>(ctx->d_stage);
+        if (ni) {
+            CU(cudaMemcpyAsync(sg + o_hash, dev.hash, ni * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(sg + o_start, dev.start, ni * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(sg + o_end, dev.end, ni * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(sg + o_rev, dev.rev, ni, cudaMemcpyDeviceToDevice, st));
+        }
+        if (nmw) CU(cudaMemcpyAsync(sg + o_mins, dev.minimizers, nmw * 16, cudaMemcpyDeviceToDevice, st));
+        if (n_off) {
+            CU(cudaMemcpyAsync(sg + o_km, dev.km_off, n_off * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(sg + o_mo, dev.min_off, n_off * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        if (n_cnt) CU(cudaMemcpyAsync(sg + o_cnt, dev.min_cnt, n_cnt * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaEventRecord(ctx->ev_done, st));
         cudaStream_t so = ctx->s_d2h;
         CU(cudaStreamWaitEvent(so, ctx->ev_done, 0));
         if (ni) {
-            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_hash) + items, dev.hash, ni * 8, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_start) + items, dev.start, ni * 4, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_end) + items, dev.end, ni * 4, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_rev) + items, dev.rev, ni, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_hash) + items, sg + o_hash, ni * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_start) + items, sg + o_start, ni * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_end) + items, sg + o_end, ni * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_rev) + items, sg + o_rev, ni, cudaMemcpyDeviceToHost, so));
         }
-        if (!L.piece) {
-            const uint64_t tail = (s + 1 == n_slabs) ? 1 : 0;              // the last slab also brings the final prefix
-            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_km_off) + r0, dev.km_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_min_off) + r0, dev.min_off, (ns + tail) * 8, cudaMemcpyDeviceToHost, so));
-            if (ns) CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_min_cnt) + r0, dev.min_cnt, ns * 4, cudaMemcpyDeviceToHost, so));
+        if (n_off) {
+            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_km_off) + r0, sg + o_km, n_off * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ptr<uint64_t>(ctx->h_min_off) + r0, sg + o_mo, n_off * 8, cudaMemcpyDeviceToHost, so));
         }
-        if (want_min && nm)
-            CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_mins) + mins * 16, dev.minimizers, nm * 16, cudaMemcpyDeviceToHost, so));
+        if (n_cnt) CU(cudaMemcpyAsync(ptr<uint32_t>(ctx->h_min_cnt) + r0, sg + o_cnt, n_cnt * 4, cudaMemcpyDeviceToHost, so));
+        if (nmw) CU(cudaMemcpyAsync(ptr<uint8_t>(ctx->h_mins) + mins * 16, sg + o_mins, nmw * 16, cudaMemcpyDeviceToHost, so));
         CU(cudaEventRecord(ctx->ev_out, so));
         items += ni; mins += nm;
         poll_release();
