@@ -96,13 +96,13 @@ struct s2k_ctx {
     int kernel_kind = 0;            // last run: always 0 (one minimizer kernel); kept for ABI stability
     // pipelined host path (s2k_run on large batches)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_out = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_free[3] = {nullptr, nullptr, nullptr}, ev_out = nullptr, ev_done = nullptr;
     bool pipe_ready = false;
     uint64_t slab_bytes = 0;        // 0 = default
-    Buf d_in[2], d_in_off[2], h_off_stage[2];
+    Buf d_in[3], d_in_off[3], h_off_stage[3];   // input slabs: one being computed, two in flight behind it
     Buf d_piece, h_piece;           // long sequences in pieces: kept-base counter and cut results
     Buf d_stage;                    // a slab's results parked for the D2H while the next slab is computed
-    Buf d_pack[2], h_pack[3];       // 2-bit transport: device landing buffers, ring of pinned staging buffers
+    Buf d_pack[3], h_pack[3];       // 2-bit transport: device landing buffers, ring of pinned staging buffers
     cudaEvent_t ev_pack[3] = {nullptr, nullptr, nullptr};
     int host_threads = 0;           // 0 = 3/4 of the hardware threads, at most 16 (measured best on a 16-core host)
     double pack_ratio = 0.7;        // share of slabs that travel packed (the rest keep PCIe busy with plain ASCII)
@@ -615,8 +615,8 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
                   &ctx->d_min_off, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
                   &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
-                  &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in_off[0], &ctx->d_in_off[1],
-                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1],
+                  &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in[2], &ctx->d_in_off[0], &ctx->d_in_off[1], &ctx->d_in_off[2],
+                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_off_stage[2], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1], &ctx->d_pack[2],
                   &ctx->h_pack[0], &ctx->h_pack[1], &ctx->h_pack[2]};
     for (Buf *b : all) release(*b);
     if (ctx->tm.created) {
@@ -625,7 +625,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
     }
     if (ctx->pipe_ready) {
         cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_free[i]); }
+        for (int i = 0; i < 3; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_free[i]); }
         cudaEventDestroy(ctx->ev_out); cudaEventDestroy(ctx->ev_done);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(ctx->ev_pack[i]);
     }
@@ -786,7 +786,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     if (!ctx->pipe_ready) {
         CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) { CU(cudaEventCreate(&ctx->ev_in[i])); CU(cudaEventCreate(&ctx->ev_free[i])); }
+        for (int i = 0; i < 3; ++i) { CU(cudaEventCreate(&ctx->ev_in[i])); CU(cudaEventCreate(&ctx->ev_free[i])); }
         CU(cudaEventCreate(&ctx->ev_out)); CU(cudaEventCreate(&ctx->ev_done));
         for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&ctx->ev_pack[i]));
         ctx->pipe_ready = true;
@@ -834,10 +834,10 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     if (any_piece) {
         if ((rc = ensure(ctx, ctx->d_piece, 64, false))) return rc;
         if ((rc = ensure(ctx, ctx->h_piece, 64, true))) return rc;
-        for (int i = 0; i < 2; ++i) if ((rc = ensure(ctx, ctx->h_off_stage[i], 16, true))) return rc;
+        for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->h_off_stage[i], 16, true))) return rc;
     }
     const size_t n_slabs = slabs.size();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if ((rc = ensure(ctx, ctx->d_in[i], max_b + 16, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_in_off[i], (max_n + 1) * 8, false))) return rc;
     }
@@ -861,11 +861,11 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     }
     const size_t np = packed_slabs.size();
     if (np) {
-        for (int i = 0; i < 2; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
+        for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
         for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->h_pack[i], max_b / 4 + 64, true))) return rc;
     }
     if (packed_in)
-        for (int i = 0; i < 2; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
+        for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
     std::vector<std::atomic<uint32_t>> pk_done(np);
     std::vector<std::atomic<uint64_t>> pk_bad(np);
     for (size_t i = 0; i < np; ++i) { pk_done[i].store(0); pk_bad[i].store(0); }
@@ -900,7 +900,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     };
 
     auto issue_h2d = [&](size_t s) -> int {
-        const int b = (int)(s & 1);
+        const int b = (int)(s % 3);
         const Slab &L = slabs[s];
         const uint64_t r0 = L.r0, r1 = L.r1, nb = L.hi - L.b0;
         const int ps = ps_of[s];
@@ -917,7 +917,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             packed = nb > 0 && pk_bad[ps].load() == 0;
         }
         STAGE(200000 + (long)s);
-        CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_free[b], 0));          // the kernels of slab s-2 are done with it
+        CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_free[b], 0));          // the kernels of slab s-3 are done with it
         ctx->tr_h2d_bytes += (packed ? (nb + 3) / 4 : nb) + (r1 - r0 + 1) * 8;
         if (packed || packed_in) ++ctx->tr_packed; else ++ctx->tr_plain;
         if (packed_in) {                                                  // the caller's packed bytes, whatever base the slab starts on
@@ -941,7 +941,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
         poll_release();
         uint64_t *d_off = ptr<uint64_t>(ctx->d_in_off[b]);
         if (L.piece) {                                                    // the piece is a sequence of its own: {0, nb}
-            uint64_t *h_off = ptr<uint64_t>(ctx->h_off_stage[b]);         // free again: slab s-2 has been through the kernels
+            uint64_t *h_off = ptr<uint64_t>(ctx->h_off_stage[b]);         // free again: slab s-3 has been through the kernels
             h_off[0] = 0; h_off[1] = nb;
             CU(cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, ctx->s_h2d));
         } else {
@@ -960,17 +960,19 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
 
     uint64_t items = 0, mins = 0;
     ctx->tr_h2d_bytes = 0; ctx->tr_packed = 0; ctx->tr_plain = 0;
-    CU(cudaEventRecord(ctx->ev_free[0], st));
-    CU(cudaEventRecord(ctx->ev_free[1], st));
+    for (int i = 0; i < 3; ++i) CU(cudaEventRecord(ctx->ev_free[i], st));
     CU(cudaEventRecord(ctx->ev_out, ctx->s_d2h));
+    // Two slabs are kept in flight behind the one being computed: run_device ends with a host synchronisation, and
+    // with a single slab queued the copy engine would idle from then until the next issue.
     if ((rc = issue_h2d(0))) return rc;
+    if (n_slabs > 1 && (rc = issue_h2d(1))) return rc;
     uint64_t seq_cnt = 0, kept_plain = 0;                  // running values of the long sequence being pieced together
     for (size_t s = 0; s < n_slabs; ++s) {
-        const int b = (int)(s & 1);
+        const int b = (int)(s % 3);
         const Slab &L = slabs[s];
         const uint64_t r0 = L.r0, r1 = L.r1, ns = r1 - r0, nb = L.hi - L.b0;
-        if (s + 1 < n_slabs) {
-            if ((rc = issue_h2d(s + 1))) return rc;
+        if (s + 2 < n_slabs) {
+            if ((rc = issue_h2d(s + 2))) return rc;
         }
         CU(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));                    // inputs of this slab have landed
         s2k_result dev;
