@@ -121,6 +121,9 @@ def cpu_port_rate(O, L, seed, mode, variant, threads, target_s=12.0, first_read=
     return nb / dt / 1e9, dt, f"{n_reads} reads x {probe_len} bp x {reps} repeats = {nb / 1e9:.3f} Gbp of the same synthetic stream, {dt:.1f} s; {impl}"
 
 
+IN_PLACE_DEFAULT = "in-place"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -131,6 +134,9 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="override the number of reads per GPU (debugging)")
     ap.add_argument("--mode", type=int, default=-1, help="override HashMode (0 Regular, 1 Hpc, 2 Simd, 3 HpcSimd)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--minimizer-stream", choices=["in-place", "ordered"], default=IN_PLACE_DEFAULT,
+                    help="ordered: also materialise the ordered minimizer stream (result.minimizers); in-place "
+                         "(S2K_NO_MINIMIZER_STREAM): the window stage reads the records where the minimizer kernel left them")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -207,9 +213,14 @@ def main():
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
 
+    in_place = args.minimizer_stream == "in-place" and not split_one      # a rank of a split sequence needs the stream
+    config["minimizer_stream"] = ("not materialised: window stage reads the records in place (S2K_NO_MINIMIZER_STREAM)"
+                                  if in_place else "ordered copy materialised (result.minimizers)")
+
     def step():
         return ctx.run_device(d_bases.data_ptr(), d_so.data_ptr(), n_reads, n_bases, L_PARAM, K_PARAM, DENSITY,
-                              S.HashMode(mode), S.HashVariant(variant), stream=stream, no_tail_rule=split_one)
+                              S.HashMode(mode), S.HashVariant(variant), stream=stream, no_tail_rule=split_one,
+                              no_minimizer_stream=in_place)
 
     def barrier():
         if world > 1:

@@ -111,6 +111,10 @@ typedef struct s2k_ctx s2k_ctx;
 #define S2K_GENERAL_KERNEL  4u  /* accepted and ignored: there is one minimizer kernel (an earlier raw-space variant that
                                    this flag bypassed was measured slower and removed) */
 #define S2K_DEBUG_TINY_CAP  8u  /* tests only: start with room for 1000 minimizers so that the grow-and-rerun path runs */
+#define S2K_NO_MINIMIZER_STREAM 16u /* s2k_run_device: do not materialise the ordered minimizer stream (result.minimizers
+                                   is NULL; items, km_off, min_off, min_cnt are unchanged).  The records stay where the
+                                   minimizer kernel appended them and the window stage reads them in place: one pass over
+                                   the records less.  Ignored for k > 12. */
 #define S2K_NO_TAIL_RULE    2u  /* do not apply the `(len-l+1) % 16 == 0` tail rule of src/nthash_avx512_32.rs:134-138:
                                    for callers that process one sequence in pieces (sharding.py) and apply the rule
                                    themselves from the length of the whole sequence */

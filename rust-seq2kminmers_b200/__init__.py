@@ -313,11 +313,14 @@ class Context:
     # -- device buffers in, device results out ------------------------------------------------------------
     def run_device(self, d_bases_ptr: int, d_seq_off_ptr: int, n_seqs: int, n_bases: int, l: int, k: int,
                    density: float, mode: HashMode, variant: HashVariant = HashVariant.NT1_32, stream: int = 0,
-                   no_tail_rule: bool = False, general_kernel: bool = False) -> _Result:
-        """Raw device-pointer form (pointers as ints).  Returns the ctypes result struct (device pointers)."""
+                   no_tail_rule: bool = False, general_kernel: bool = False, no_minimizer_stream: bool = False) -> _Result:
+        """Raw device-pointer form (pointers as ints).  Returns the ctypes result struct (device pointers).
+        no_minimizer_stream (S2K_NO_MINIMIZER_STREAM): result.minimizers is NULL, the window stage reads the minimizer
+        records in place (one pass over them less); everything else in the result is unchanged."""
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
-        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (2 if no_tail_rule else 0) | (4 if general_kernel else 0)))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (2 if no_tail_rule else 0) | (4 if general_kernel else 0) |
+                                                 (16 if no_minimizer_stream else 0)))
         try:
             self._check(self.lib.c.s2k_run_device(self.h, C.c_void_p(d_bases_ptr), C.c_void_p(d_seq_off_ptr), int(n_seqs),
                                                   int(n_bases), C.byref(p), C.c_void_p(stream), C.byref(r)))

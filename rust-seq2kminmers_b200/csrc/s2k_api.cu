@@ -88,7 +88,7 @@ struct s2k_ctx {
     double rate_hint = 0.0;         // observed minimizers per base (grow-only)
     // device buffers
     Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_hpc_off, d_km_off, d_min_cnt;
-    Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr, d_tmp, d_tile_info, d_tile_base;
+    Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr, d_tmp, d_tile_info, d_tile_base, d_tile_src;
     // pinned host result buffers
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
@@ -344,9 +344,12 @@ void timing_prepare(s2k_ctx *ctx)
 
 // d_small layout (uint64 words): [0] record cursor, [4] ticket(u32), [5] err(u32), [6] ticket2(u32)
 // Runs the whole device pipeline on `st`.  On return the totals have been read back (one sync).
+// in_place_ok: the caller does not need the ordered minimizer stream on the device.  With S2K_NO_MINIMIZER_STREAM set the
+// records then stay where k_minimizers appended them and the window stage reads them through a per-tile index.
 int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs, uint64_t n_bases,
-               const Plan &P, cudaStream_t st, s2k_result *out)
+               const Plan &P, cudaStream_t st, s2k_result *out, bool in_place_ok = false)
 {
+    const bool in_place = in_place_ok && (ctx->flags & S2K_NO_MINIMIZER_STREAM) && P.k <= (uint32_t)KW_MAX;
     int rc;
     if ((rc = set_attrs(ctx)) != S2K_OK) return rc;
     timing_prepare(ctx);
@@ -450,7 +453,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         cap = std::max(cap, n_min);                    // exact size known now: rerun once, with one global allocator
         regions = false;
     }
-    if ((rc = ensure(ctx, ctx->d_mins, std::max<uint64_t>(n_min, 1) * sizeof(uint4), false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_mins, (in_place ? 1 : std::max<uint64_t>(n_min, 1)) * sizeof(uint4), false))) return rc;
+    if (in_place && (rc = ensure(ctx, ctx->d_tile_src, (uint64_t)n_tiles * sizeof(ulonglong2), false))) return rc;
     {
         const uint32_t n_chunks = (n_tiles + ST - 1) / ST;
         // d_tile_base: [tile_loc u64 x n_tiles][chunk_tot u64 x n_chunks][chunk_base u64x2 x (n_chunks+1)]
@@ -466,6 +470,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         F.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
         F.min_off = ptr<uint64_t>(ctx->d_min_off); F.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
         F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = tmp_records; F.n_tiles = n_tiles; F.tile = tile_eff;
+        F.tile_src = in_place ? ptr<ulonglong2>(ctx->d_tile_src) : nullptr; F.copy = in_place ? 0 : 1;
         const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 8);
         S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
         CU(cudaGetLastError());
@@ -481,7 +486,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     if ((rc = ensure(ctx, ctx->d_rev, item_cap, false))) return rc;
     {
         K2Args B;
-        B.mins = ptr<uint4>(ctx->d_mins);
+        B.mins = in_place ? ptr<uint4>(ctx->d_tmp) : ptr<uint4>(ctx->d_mins);
+        B.tile_src = in_place ? ptr<ulonglong2>(ctx->d_tile_src) : nullptr; B.n_tiles = n_tiles; B.tile = tile_eff;
         B.min_off = ptr<uint64_t>(ctx->d_min_off);
         B.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
         B.seq_off = d_seq_off; B.bases = d_bases; B.n_seqs = n_seqs;
@@ -503,7 +509,19 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         C.mins = B.mins; C.min_off = B.min_off; C.km_off = B.km_off; C.n_min = n_min; C.k = P.k;
         C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);
         C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
-        if (n_min > 0) {
+        if (n_min > 0 && in_place) {
+            K3TArgs D;
+            D.W = C; D.tile_info = ptr<uint4>(ctx->d_tile_info); D.tile_src = B.tile_src; D.n_tiles = n_tiles;
+            const int g3 = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 16);
+            switch ((int)P.k) {
+#define S2K_WINDOWS_CASE(K) case K: S2K_LAUNCH(k_windows_t<K>, g3, 256, 0, st, false, D); break;
+                S2K_WINDOWS_CASE(1) S2K_WINDOWS_CASE(2) S2K_WINDOWS_CASE(3) S2K_WINDOWS_CASE(4) S2K_WINDOWS_CASE(5) S2K_WINDOWS_CASE(6)
+                S2K_WINDOWS_CASE(7) S2K_WINDOWS_CASE(8) S2K_WINDOWS_CASE(9) S2K_WINDOWS_CASE(10) S2K_WINDOWS_CASE(11) S2K_WINDOWS_CASE(12)
+#undef S2K_WINDOWS_CASE
+            }
+            CU(cudaGetLastError());
+            ctx->launches += 1;
+        } else if (n_min > 0) {
             const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 16);
             switch (P.k <= (uint32_t)KW_MAX ? (int)P.k : 0) {
 #define S2K_WINDOWS_CASE(K) case K: S2K_LAUNCH(k_windows_w<K>, g3, 256, 0, st, false, C); break;
@@ -536,7 +554,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     out->end = ptr<uint32_t>(ctx->d_end);
     out->rev = ptr<uint8_t>(ctx->d_rev);
     out->km_off = ptr<uint64_t>(ctx->d_km_off);
-    out->minimizers = reinterpret_cast<const s2k_minimizer *>(ctx->d_mins.p);
+    out->minimizers = in_place ? nullptr : reinterpret_cast<const s2k_minimizer *>(ctx->d_mins.p);
     out->min_off = ptr<uint64_t>(ctx->d_min_off);
     out->min_cnt = ptr<uint32_t>(ctx->d_min_cnt);
     return S2K_OK;
@@ -613,7 +631,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     Buf *all[] = {&ctx->d_bases, &ctx->d_seq_off, &ctx->d_tile_lb, &ctx->d_status, &ctx->d_small, &ctx->d_mins,
                   &ctx->d_min_off, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
-                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
+                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->d_tile_src, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in[2], &ctx->d_in_off[0], &ctx->d_in_off[1], &ctx->d_in_off[2],
                   &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_off_stage[2], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1], &ctx->d_pack[2],
@@ -708,7 +726,7 @@ int s2k_run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_o
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
     ctx->err.clear();
-    return run_device(ctx, d_bases, d_seq_off, n_seqs, n_bases, P, st, out);
+    return run_device(ctx, d_bases, d_seq_off, n_seqs, n_bases, P, st, out, true);
 }
 
 int s2k_ctx_set_transport(s2k_ctx *ctx, int host_threads, double pack_ratio)

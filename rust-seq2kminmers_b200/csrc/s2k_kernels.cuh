@@ -872,6 +872,8 @@ struct KFArgs {
     uint64_t *min_off, *hpc_off;
     uint64_t n_seqs, n_bases, min_cap;
     uint32_t n_tiles, tile;
+    ulonglong2 *tile_src;        // or null: per tile (ordered index of its first record, where its records sit in tmp)
+    int32_t copy;                // 0: leave the records where they are (the window stage reads them through tile_src)
 };
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs A)
 {
@@ -883,7 +885,8 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs
         const unsigned long long loc = A.tile_loc[t];
         const uint64_t bm = cb.x + (loc & 0xffffffffull), bk = cb.y + (loc >> 32);
         const uint64_t src = ((uint64_t)info.w << 32) | info.z;
-        if (src + info.x <= A.min_cap)
+        if (A.tile_src && lane == 0) A.tile_src[t] = make_ulonglong2(bm, src);
+        if (A.copy && src + info.x <= A.min_cap)
             for (uint32_t j = lane; j < info.x; j += 32) A.mins[bm + j] = A.tmp[src + j];
         const bool last_tile = (uint64_t)(t + 1) * A.tile >= A.n_bases;
         const uint32_t lb = A.tile_lb[t], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
@@ -909,7 +912,19 @@ struct K2Args {
     uint64_t *status;              // per tile, zeroed
     uint32_t *ticket;
     uint32_t *err;
+    const ulonglong2 *tile_src;    // non-null: `mins` is the unordered record store of k_minimizers (tiles contiguous,
+    uint32_t  n_tiles, tile;       // in completion order) and ordered index m is looked up through tile_src
 };
+
+// Tile holding ordered record m: the largest t with tile_src[t].x <= m.  `hint` is a tile near it (the caller knows a
+// base position close to the minimizer); the walk is a step or two except across runs of tiles without minimizers.
+__device__ __forceinline__ uint32_t tile_of_record(const ulonglong2 *tile_src, uint32_t n_tiles, uint64_t m, uint32_t hint)
+{
+    uint32_t t = hint < n_tiles ? hint : n_tiles - 1;
+    while (t > 0 && tile_src[t].x > m) --t;
+    while (t + 1 < n_tiles && tile_src[t + 1].x <= m) ++t;
+    return t;
+}
 
 // Minimizers of sequence r that reach the window stage.  In the AVX-512 profile of ntHash1 the iterator
 // masks the last block with (1 << (S % 16)) - 1 (src/nthash_avx512_32.rs:134-138): when S > 16 and
@@ -935,7 +950,18 @@ __device__ __forceinline__ uint32_t window_feed_count(const K2Args &A, uint64_t 
                 }
                 e16 = g - so;
             }
-            while (cnt > 0 && (uint64_t)A.mins[m0 + cnt - 1].z >= e16) --cnt;
+            if (!A.tile_src) {
+                while (cnt > 0 && (uint64_t)A.mins[m0 + cnt - 1].z >= e16) --cnt;
+            } else {
+                uint32_t t = (uint32_t)((se - 1) / A.tile);
+                while (cnt > 0) {
+                    const uint64_t m = m0 + cnt - 1;
+                    t = tile_of_record(A.tile_src, A.n_tiles, m, t);
+                    const ulonglong2 ts = A.tile_src[t];
+                    if ((uint64_t)A.mins[ts.y + (m - ts.x)].z < e16) break;
+                    --cnt;
+                }
+            }
         }
     }
     return (uint32_t)cnt;
@@ -1106,6 +1132,53 @@ __global__ void __launch_bounds__(256) k_windows_w(const __grid_constant__ K3Arg
                 A.start[o] = rec.y;
                 A.end[o] = end;
                 A.rev[o] = r < f;
+            }
+        }
+    }
+}
+// The same window stage reading the records where k_minimizers left them (no ordered copy, S2K_NO_MINIMIZER_STREAM):
+// one warp per tile; the last K-1 windows of a tile look into the following tiles.
+struct K3TArgs {
+    K3Args W;                       // W.mins = the unordered record store
+    const uint4 *tile_info;
+    const ulonglong2 *tile_src;
+    uint32_t n_tiles;
+};
+template <int K>
+__global__ void __launch_bounds__(256) k_windows_t(const __grid_constant__ K3TArgs A)
+{
+    constexpr uint32_t OUT = 32 - (K - 1);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < A.n_tiles; t += nwarps) {
+        const uint32_t h = A.tile_info[t].x;
+        if (h == 0) continue;
+        const ulonglong2 ts = A.tile_src[t];
+        for (uint32_t p0 = 0; p0 < h; p0 += OUT) {
+            const uint32_t j = p0 + lane;
+            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+            if (j < h) {
+                rec = A.W.mins[ts.y + j];
+            } else if (j - h < (uint32_t)(K - 1) && ts.x + j < A.W.n_min) {
+                const uint64_t m = ts.x + j;
+                const uint32_t t2 = tile_of_record(A.tile_src, A.n_tiles, m, t + 1);
+                const ulonglong2 ts2 = A.tile_src[t2];
+                rec = A.W.mins[ts2.y + (m - ts2.x)];
+            }
+            uint64_t f = 0, r = 0;
+            WindowFold<K, 0>::run(mix32(rec.x), f, r);
+            const uint32_t end = K > 1 ? __shfl_down_sync(0xffffffffu, rec.z, K - 1) : rec.z;
+            if (lane < OUT && j < h) {
+                const uint32_t rid = rec.w;
+                const uint64_t c = ts.x + j - A.W.min_off[rid];
+                const uint64_t k0 = A.W.km_off[rid];
+                if (c < A.W.km_off[rid + 1] - k0) {
+                    const uint64_t o = k0 + c;
+                    A.W.hash[o] = f < r ? f : r;
+                    A.W.start[o] = rec.y;
+                    A.W.end[o] = end;
+                    A.W.rev[o] = r < f;
+                }
             }
         }
     }

@@ -92,3 +92,21 @@ def fuzz_cases(B, n_cases, max_len):
         bases, so = B.batch(lens, alphabet=alphabet, runp=runp)
         out.append((bases, so, (l, k, d, mode, variant)))
     return out
+
+
+def run_device_in_place(S, ctx, bases, so, l, k, d, mode, var, to_device, to_host):
+    """s2k_run_device with S2K_NO_MINIMIZER_STREAM on a batch held by the caller: `to_device(np array) -> (handle, ptr)`
+    puts an array where the context's kernels can read it, `to_host(ptr, nbytes) -> np.uint8 array` reads results back.
+    Returns a KminmersBatch without a minimizer stream."""
+    n = len(so) - 1
+    pad = np.zeros(len(bases) + 16, dtype=np.uint8)
+    pad[:len(bases)] = bases
+    hb, pb = to_device(pad)
+    ho, po = to_device(np.ascontiguousarray(so, dtype=np.uint64))
+    r = ctx.run_device(pb, po, n, len(bases), l, k, d, S.HashMode(mode), S.HashVariant(var), no_minimizer_stream=True)
+    assert not r.minimizers or k > 12            # NULL: the ordered stream was not materialised
+    ni = int(r.n_items)
+    get = lambda p, c, dt: to_host(p, c * np.dtype(dt).itemsize).view(dt).copy() if c else np.zeros(0, dt)
+    return S.KminmersBatch(n, get(r.hash, ni, np.uint64), get(r.start, ni, np.uint32), get(r.end, ni, np.uint32),
+                           get(r.rev, ni, np.uint8), get(r.km_off, n + 1, np.uint64), get(r.min_off, n + 1, np.uint64),
+                           get(r.min_cnt, n, np.uint32), int(r.n_minimizers), None)

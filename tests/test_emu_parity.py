@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_batch_matches_oracle
-from parity_cases import cases, fuzz_cases
+from parity_cases import cases, fuzz_cases, run_device_in_place
 
 
 def test_emulated_kernels_match_oracle(S, O, emu_ctx, batches, fixture_seq):
@@ -152,3 +152,27 @@ def test_capacity_overflow_reruns_emulated(S, O, emu_ctx, batches):
     got = emu_ctx.run(bases, so, 15, 3, 0.3, S.HashMode.Hpc, want_minimizers=True, debug_tiny_cap=True)
     assert got.n_minimizers > 1000
     assert_batch_matches_oracle(O, got, bases, so, 15, 3, 0.3, 1)
+
+
+def test_window_stage_in_place_emulated(S, O, emu_ctx, batches, fixture_seq):
+    """S2K_NO_MINIMIZER_STREAM: the window stage and the tail rule read the minimizer records where the minimizer kernel
+    left them (tiles in completion order) -- same items, offsets and counts as the ordered path."""
+    import ctypes
+    keep = []
+    def to_device(a):
+        keep.append(a)
+        return a, a.ctypes.data
+    to_host = lambda p, nb: np.frombuffer((ctypes.c_uint8 * nb).from_address(p), dtype=np.uint8)
+    for label, bases, so, params in cases(batches, fixture_seq, scale=1):
+        if label in ("big-l", "non-ACGT"):
+            continue
+        for (l, k, d, mode, var) in params[:8]:
+            got = run_device_in_place(S, emu_ctx, bases, so, l, k, d, mode, var, to_device, to_host)
+            assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
+            ref = emu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var))
+            assert np.array_equal(got.min_off, ref.min_off) and np.array_equal(got.min_cnt, ref.min_cnt), label
+    # sparse selection over many tiles: windows whose k minimizers span several tiles, tiles without any minimizer
+    bases, so = batches.batch([120000, 150, 90000])
+    for (l, k, d, mode) in [(31, 12, 0.0005, 3), (31, 5, 0.0002, 2), (15, 9, 0.001, 1), (31, 3, 0.00005, 0)]:
+        got = run_device_in_place(S, emu_ctx, bases, so, l, k, d, mode, 0, to_device, to_host)
+        assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, 0)

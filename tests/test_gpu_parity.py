@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_batch_matches_oracle
-from parity_cases import cases, fuzz_cases
+from parity_cases import cases, fuzz_cases, run_device_in_place
 
 pytestmark = pytest.mark.gpu
 
@@ -287,3 +287,43 @@ def test_contexts_on_concurrent_host_threads(S, O, batches):
     assert not errors, errors
     for i in range(4):
         assert_batch_matches_oracle(O, results[i], work[i][0], work[i][1], 31, 5, 0.02, int(work[i][2]))
+
+
+def test_window_stage_in_place(S, O, gpu_ctx, batches, fixture_seq):
+    """S2K_NO_MINIMIZER_STREAM through s2k_run_device: the window stage and the tail rule read the minimizer records
+    where k_minimizers appended them (per-CTA regions, tiles in completion order).  Same tuples as the oracle, same
+    min_off / min_cnt as the ordered path; then config-2 geometry against the ordered path item by item."""
+    import torch
+    dev = torch.device("cuda:0")
+
+    def to_device(a):
+        t = torch.from_numpy(a.view(np.uint8).copy()).to(dev)
+        return t, t.data_ptr()
+    to_host = lambda p, nb: torch.as_tensor(S.DeviceArray(p, nb, "|u1"), device=dev).cpu().numpy()
+    for label, bases, so, params in cases(batches, fixture_seq, scale=4):
+        if label == "big-l":
+            continue
+        for (l, k, d, mode, var) in params:
+            got = run_device_in_place(S, gpu_ctx, bases, so, l, k, d, mode, var, to_device, to_host)
+            assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
+            ref = gpu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var))
+            assert np.array_equal(got.min_off, ref.min_off) and np.array_equal(got.min_cnt, ref.min_cnt), label
+    bases, so = batches.batch([1200000, 150, 900000])
+    for (l, k, d, mode) in [(31, 12, 0.0005, 3), (31, 5, 0.0002, 2), (15, 9, 0.001, 1), (31, 3, 0.00005, 0)]:
+        got = run_device_in_place(S, gpu_ctx, bases, so, l, k, d, mode, 0, to_device, to_host)
+        assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, 0)
+    # config-2 geometry, 0.4 Gbp: every item equal to the ordered path
+    L, n = 20000, 20000
+    d_bases = torch.empty(L * n + 16, dtype=torch.uint8, device=dev)
+    gpu_ctx.synth_device(0x5EED0002, 0, L * n, d_bases.data_ptr())
+    d_so = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
+    outs = []
+    for flag in (False, True):
+        r = gpu_ctx.run_device(d_bases.data_ptr(), d_so.data_ptr(), n, n * L, 31, 5, 0.01, S.HashMode.HpcSimd,
+                               no_minimizer_stream=flag)
+        t = lambda p, c, isz: torch.as_tensor(S.DeviceArray(p, c * isz, "|u1"), device=dev).clone()
+        outs.append((int(r.n_items), t(r.hash, r.n_items, 8), t(r.start, r.n_items, 4), t(r.end, r.n_items, 4),
+                     t(r.rev, r.n_items, 1), t(r.km_off, n + 1, 8), t(r.min_off, n + 1, 8), t(r.min_cnt, n, 4)))
+    assert outs[0][0] == outs[1][0] > 0
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert torch.equal(a, b)
