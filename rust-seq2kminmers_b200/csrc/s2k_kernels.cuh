@@ -733,6 +733,13 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 #pragma unroll
                 for (int x = 0; x < MW; ++x) {
                     unsigned long long m = S.hitw[pass][tid][x];
+                    if (tile_min <= (uint32_t)HL) {        // the usual case, one round: no range test, 32-bit halves
+                        uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32);
+                        const uint32_t v0 = (uint32_t)(pass * CAP + CH * tid + 64 * x);
+                        while (mlo) { S.hl[o++] = (uint16_t)(v0 + (uint32_t)__ffs((int)mlo) - 1u); mlo &= mlo - 1u; }
+                        while (mhi) { S.hl[o++] = (uint16_t)(v0 + 31u + (uint32_t)__ffs((int)mhi)); mhi &= mhi - 1u; }
+                        continue;
+                    }
                     while (m) {
                         const int i = __ffsll((long long)m) - 1 + 64 * x;
                         m &= m - 1;
@@ -917,12 +924,25 @@ struct K2Args {
 };
 
 // Tile holding ordered record m: the largest t with tile_src[t].x <= m.  `hint` is a tile near it (the caller knows a
-// base position close to the minimizer); the walk is a step or two except across runs of tiles without minimizers.
+// base position close to the minimizer): a step or two, except across runs of tiles without minimizers (a homopolymer
+// of megabases), where the walk turns into a binary search after 8 steps.
 __device__ __forceinline__ uint32_t tile_of_record(const ulonglong2 *tile_src, uint32_t n_tiles, uint64_t m, uint32_t hint)
 {
     uint32_t t = hint < n_tiles ? hint : n_tiles - 1;
-    while (t > 0 && tile_src[t].x > m) --t;
-    while (t + 1 < n_tiles && tile_src[t + 1].x <= m) ++t;
+    for (int steps = 0; t > 0 && tile_src[t].x > m; --t) {
+        if (++steps > 8) {
+            uint32_t lo = 0, hi = t;                       // tile_src[lo].x <= m < tile_src[hi].x
+            while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (tile_src[mid].x <= m) lo = mid; else hi = mid; }
+            return lo;                                     // nothing above lo qualifies
+        }
+    }
+    for (int steps = 0; t + 1 < n_tiles && tile_src[t + 1].x <= m; ++t) {
+        if (++steps > 8) {
+            uint32_t lo = t + 1, hi = n_tiles;             // tile_src[lo].x <= m; hi = one past the last tile
+            while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (tile_src[mid].x <= m) lo = mid; else hi = mid; }
+            return lo;
+        }
+    }
     return t;
 }
 

@@ -110,3 +110,21 @@ def run_device_in_place(S, ctx, bases, so, l, k, d, mode, var, to_device, to_hos
     return S.KminmersBatch(n, get(r.hash, ni, np.uint64), get(r.start, ni, np.uint32), get(r.end, ni, np.uint32),
                            get(r.rev, ni, np.uint8), get(r.km_off, n + 1, np.uint64), get(r.min_off, n + 1, np.uint64),
                            get(r.min_cnt, n, np.uint32), int(r.n_minimizers), None)
+
+
+def empty_tile_cases(B, n_poly=400000, l=31):
+    """Homopolymers of hundreds of kilobases: more than eight consecutive tiles without any minimizer in the HPC modes
+    (the index walks of the in-place window stage turn into binary searches) -- in the middle of a sequence (windows
+    spanning the gap) and at the end of two sequences whose head lengths are chosen so that the AVX-512 tail rule
+    (S > 16 and S % 16 == 0 in HPC space) fires on the first and not on the second."""
+    poly = np.full(n_poly, ord("A"), np.uint8)
+    head = B.seq(4000)
+    kept = lambda s: 1 + int(np.count_nonzero(s[1:] != s[:-1]))
+    seqs = [np.concatenate([head, poly, B.seq(3000)])]
+    n = 3000
+    while (kept(np.concatenate([head[:n], poly[:8]])) - l + 1) % 16 != 0:
+        n += 1
+    seqs += [np.concatenate([head[:n], poly]), np.concatenate([head[:n + 1], poly]), B.seq(500)]
+    if head[n] == ord("A"):                                # n + 1 would not add a kept base
+        seqs[2] = np.concatenate([head[:n + 2], poly])
+    return B.pack(seqs)

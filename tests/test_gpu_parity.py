@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_batch_matches_oracle
-from parity_cases import cases, fuzz_cases, run_device_in_place
+from parity_cases import cases, empty_tile_cases, fuzz_cases, run_device_in_place
 
 pytestmark = pytest.mark.gpu
 
@@ -312,6 +312,10 @@ def test_window_stage_in_place(S, O, gpu_ctx, batches, fixture_seq):
     for (l, k, d, mode) in [(31, 12, 0.0005, 3), (31, 5, 0.0002, 2), (15, 9, 0.001, 1), (31, 3, 0.00005, 0)]:
         got = run_device_in_place(S, gpu_ctx, bases, so, l, k, d, mode, 0, to_device, to_host)
         assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, 0)
+    bases, so = empty_tile_cases(batches)                 # long runs of tiles without minimizers (index walks -> binary search)
+    for (l, k, d, mode) in [(31, 5, 0.01, 3), (31, 12, 0.02, 3), (21, 3, 0.01, 1)]:
+        got = run_device_in_place(S, gpu_ctx, bases, so, l, k, d, mode, 0, to_device, to_host)
+        assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, 0, check_minimizers=False)
     # config-2 geometry, 0.4 Gbp: every item equal to the ordered path
     L, n = 20000, 20000
     d_bases = torch.empty(L * n + 16, dtype=torch.uint8, device=dev)
