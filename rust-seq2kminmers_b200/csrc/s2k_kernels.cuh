@@ -255,8 +255,10 @@ __device__ __forceinline__ int chunk_of(const Smem &S, int q)
     return c;
 }
 // Original-space position (global index into `bases`) of kept base q that lies in chunk c.
+template <bool LUT>
 __device__ __forceinline__ int64_t pos_in_chunk(const Smem &S, int64_t W0, int c, int q)
 {
+    if (!LUT) return W0 + 32 * c + nth_set_bit(S.keepw[c], q - (int)S.qoff[c]);   // HPC off: measured faster (registers)
     // select in two halving steps and one table look-up (the five-step form costs about twice the instructions)
     uint32_t w = S.keepw[c];
     int r = q - (int)S.qoff[c], pos = 0;
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     uint32_t *const hs = A.hscr + (size_t)blockIdx.x * WIN;
 
     for (int i = tid; i < 256; i += NT) S.lut[i] = A.cls_lut[i];
-    for (int i = tid; i < 256 * 8; i += NT) {
+    for (int i = tid; HPC && i < 256 * 8; i += NT) {        // the table-assisted select serves the HPC variants only
         uint32_t b = (uint32_t)i >> 3;
         for (int r = i & 7; r > 0 && b; --r) b &= b - 1u;      // drop the r lowest set bits
         S.sel8[i] = (uint8_t)(b ? __ffs((int)b) - 1 : 0);
@@ -770,11 +772,11 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 const int qo = hk + v;                     // window index of the owner base
                 const uint32_t h = hs[v];
                 int c = chunk_of(S, qo);
-                const int64_t g_own = pos_in_chunk(S, W0, c, qo);
+                const int64_t g_own = pos_in_chunk<HPC>(S, W0, c, qo);
                 const int qs = qo - (l - 1 + d);           // first base of the l-mer: a little further left
                 int64_t g_start;
                 if (qs < 0) g_start = W0 - (int64_t)S.ctxpos[-1 - qs];
-                else { while ((int)S.qoff[c] > qs) --c; g_start = pos_in_chunk(S, W0, c, qs); }
+                else { while ((int)S.qoff[c] > qs) --c; g_start = pos_in_chunk<HPC>(S, W0, c, qs); }
                 uint32_t lo = lb, hi = ub;                 // first i in [lb,ub) with seq_off[i] > g_own
                 while (lo < hi) {
                     const uint32_t mid = lo + ((hi - lo) >> 1);
