@@ -271,8 +271,8 @@ def main():
     peak, peak_src = peaks()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # DRAM traffic of the kernel from the committed `ncu --set full` capture (profiles/r1_final_kernel_summary.txt:
-    # 1.1087 GB read + 0.3217 GB written for a 1.000 Gbp launch of this workload shape), scaled to this launch.
-    traffic = (1.1087e9 + 0.3217e9) * (n_bases / 1e9) if args.workload == "c2" and mode == 3 and variant == 0 else None
+    # 1.1076 GB read + 0.3191 GB written for a 1.000 Gbp launch of this workload shape), scaled to this launch.
+    traffic = (1.1076e9 + 0.3191e9) * (n_bases / 1e9) if args.workload == "c2" and mode == 3 and variant == 0 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_final_kernel_summary.txt, scaled by bases" if traffic else None,
                 "algorithmic_bytes": alg_bytes,
@@ -285,7 +285,7 @@ def main():
         mhz = float(clocks.get("sm_mhz") or 1965.0) if isinstance(clocks, dict) else 1965.0
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         issue_peak = sms * 4 * 32 * mhz * 1e6            # thread-instructions per second
-        ipb, alu_share = 35.3, 0.52
+        ipb, alu_share = 35.1, 0.52
         rate = n_bases / (k_ms * 1e-3)
         roofline["instruction_bound"] = {"thread_instr_per_base": ipb, "source": "profiles/r1_final_kernel_summary.txt",
                                          "issue_frac": rate * ipb / issue_peak, "alu_pipe_frac": rate * ipb * alu_share / (issue_peak / 2)}
