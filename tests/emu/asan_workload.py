@@ -17,4 +17,15 @@ for mode, var, l in [(3, 0, 31), (1, 0, 31), (2, 0, 31), (0, 0, 31), (3, 1, 31),
 ctx.set_slab_bytes(30000)
 r = ctx.run(bases, so, 31, 5, 0.02, S.HashMode.HpcSimd, want_minimizers=True)
 h, p, off = ctx.encode_rle(bases, so)
+# device API with S2K_NO_MINIMIZER_STREAM: the window stage and the tail rule read the records in place (tile index walks)
+import ctypes
+so_dev = so.copy()
+for mode, k, d in [(3, 5, 0.05), (3, 12, 0.002), (2, 3, 0.5), (1, 2, 0.01), (0, 7, 0.0005)]:
+    want = ctx.run(bases, so, 31, k, d, S.HashMode(mode))
+    rd = ctx.run_device(bases.ctypes.data, so_dev.ctypes.data, len(so) - 1, len(bases), 31, k, d, S.HashMode(mode),
+                        no_minimizer_stream=True)
+    assert not rd.minimizers and int(rd.n_items) == want.n_items, (mode, k, d)
+    got = np.frombuffer((ctypes.c_uint64 * int(rd.n_items)).from_address(rd.hash), dtype=np.uint64) if rd.n_items else np.zeros(0, np.uint64)
+    assert np.array_equal(got, want.hash), (mode, k, d)
+    print("ok in place", mode, k, d, int(rd.n_items))
 print("asan workload done", r.n_items, len(h))
