@@ -166,7 +166,7 @@ def test_window_stage_in_place_emulated(S, O, emu_ctx, batches, fixture_seq):
     for label, bases, so, params in cases(batches, fixture_seq, scale=1):
         if label in ("big-l", "non-ACGT"):
             continue
-        for (l, k, d, mode, var) in params[:8]:
+        for (l, k, d, mode, var) in params[:5]:
             got = run_device_in_place(S, emu_ctx, bases, so, l, k, d, mode, var, to_device, to_host)
             assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, var)
             ref = emu_ctx.run(bases, so, l, k, d, S.HashMode(mode), S.HashVariant(var))
