@@ -449,6 +449,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         n_min = hsmall[0];
+        if ((uint32_t)hsmall[2] & ERR_ALIGN) return fail(ctx, S2K_ERR_INTERNAL, "shared-memory tables are not 256-byte aligned");
         if (regions ? !((uint32_t)hsmall[2] & ERR_CAP) : n_min <= cap) break;
         cap = std::max(cap, n_min);                    // exact size known now: rerun once, with one global allocator
         regions = false;
@@ -792,13 +793,13 @@ struct Slab {
 // packed_in: `bases` is the caller's 2-bit packed batch (s2k_run_packed2) -- slabs are copied as they are and unpacked
 // on the device; the host packers stay idle.
 static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const Plan &P,
-                         uint64_t slab_bytes, uint64_t overlap, bool &overlap_short, s2k_result *out, bool packed_in)
+                         uint64_t slab_bytes, uint64_t overlap, int &overlap_short, s2k_result *out, bool packed_in)
 {
     int rc;
     auto base_at = [&](uint64_t i) -> uint8_t {             // equality of bases is all the host ever asks
         return packed_in ? (uint8_t)((bases[i >> 2] >> (2 * (i & 3))) & 3u) : bases[i];
     };
-    overlap_short = false;
+    overlap_short = 0;                                     // 1: redo with a longer overlap, 2: only the one-shot run will do
     stage_watchdog();
     STAGE(1);
     if (!ctx->pipe_ready) {
@@ -822,11 +823,28 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
         const uint64_t len0 = seq_off[r0 + 1] - seq_off[r0];
         if (len0 > slab_bytes + slab_bytes / 2 && len0 > (uint64_t)P.l) {
             const uint64_t s0 = seq_off[r0], s1 = seq_off[r0 + 1];
+            // The AVX-512 tail rule (src/nthash_avx512_32.rs:134-138) drops the minimizers that END in the last 16 kept
+            // bases; they START within the last l+15 kept bases.  Only the LAST piece knows whether the rule fired (it
+            // needs the kept-base count of the whole sequence), so it must own every one of them, and k-1 surviving
+            // minimizers before them for the windows the piece before it owns (checked when the rule fires): no cut
+            // after `tail_lo` = the (l+16)-th kept base from the end, moved left by the overlap and onto a run start.
+            // A homopolymer or no-run tail longer than a piece makes the last piece longer, not the result wrong.
+            uint64_t tail_lo = s1;
+            if (P.quirk) {
+                uint64_t left = (uint64_t)P.l + 16;
+                while (left && tail_lo > s0) {
+                    --tail_lo;
+                    if (!P.hpc || tail_lo == s0 || base_at(tail_lo) != base_at(tail_lo - 1)) --left;
+                }
+                tail_lo = tail_lo - s0 > overlap ? tail_lo - overlap : s0;
+                if (P.hpc) while (tail_lo > s0 && base_at(tail_lo) == base_at(tail_lo - 1)) --tail_lo;
+            }
             uint64_t b0 = s0;
             while (b0 < s1) {
                 uint64_t b1 = std::min(s1, b0 + std::min<uint64_t>(slab_bytes, 1ull << 31));
                 if (s1 - b1 < slab_bytes / 2) b1 = s1;                          // no tiny last piece
                 if (P.hpc) while (b1 < s1 && base_at(b1) == base_at(b1 - 1)) ++b1;  // cut on a run boundary
+                if (b1 < s1 && b1 > tail_lo) b1 = tail_lo > b0 ? tail_lo : s1;  // tail_lo is a kept base: a run boundary
                 const uint64_t hi = b1 == s1 ? s1 : std::min(s1, b1 + overlap);
                 slabs.push_back(Slab{r0, r0 + 1, true, b0 == s0, b1 == s1, b0, b1, hi});
                 max_b = std::max(max_b, hi - b0);
@@ -1040,7 +1058,7 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
                 if (rule) {                                               // 16th kept base from the end of the sequence
                     uint64_t pos = s1, left = 16;
                     while (left && pos > s0) { --pos; if (!P.hpc || pos == s0 || base_at(pos) != base_at(pos - 1)) --left; }
-                    if (pos <= L.b0) { overlap_short = true; return S2K_OK; }   // a homopolymer tail as long as a piece
+                    if (pos <= L.b0) { overlap_short = 2; return S2K_OK; }     // cannot happen: no cut after tail_lo
                     e16 = pos - L.b0;
                 }
             }
@@ -1050,7 +1068,9 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             ctx->launches += 2;
             const uint64_t n_keep = rule ? hp[3] : n_min;
             const uint64_t i1 = L.last ? n_keep : hp[2];
-            if (!L.last && i1 + P.k + 3 > n_min) { overlap_short = true; return S2K_OK; }   // windows near b1 lack followers
+            if (!L.last && i1 + P.k + 3 > n_min) { overlap_short = 1; return S2K_OK; }   // windows near b1 lack followers
+            // the last windows of the piece before this one reach k-1 minimizers into it: all of them must have survived
+            if (rule && !L.first && n_keep + 1 < P.k) { overlap_short = 2; return S2K_OK; }
             const uint64_t n_win = n_keep >= P.k ? n_keep - P.k + 1 : 0;
             ni = std::min(i1, n_win);
             nm = L.last ? n_min : i1;
@@ -1172,11 +1192,16 @@ static int run_host(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off,
             const double frac = std::max(1e-9, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
             uint64_t overlap = (uint64_t)std::min(4.0e9, 64.0 * (P.k + 8.0) / frac + 64.0 * P.l + 4096.0);
             for (int attempt = 0; attempt < 3; ++attempt) {
-                bool too_short = false;
+                int too_short = 0;
                 rc = run_pipelined(ctx, bases, seq_off, n_seqs, P, slab, overlap, too_short, out, packed_in);
-                if (rc != S2K_OK || !too_short) return rc;
+                if (rc != S2K_OK || !too_short) {
+                    // on an error, copies from the caller's buffers may still be queued: do not hand the buffers back early
+                    if (rc != S2K_OK && ctx->pipe_ready) { cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_d2h); cudaStreamSynchronize(st); }
+                    return rc;
+                }
                 STAGE(700000 + attempt);
                 CU(cudaStreamSynchronize(ctx->s_h2d)); CU(cudaStreamSynchronize(ctx->s_d2h)); CU(cudaStreamSynchronize(st));
+                if (too_short == 2) break;                 // a longer overlap would not help
                 overlap = std::min<uint64_t>(n_bases, overlap * 8);
             }                                              // still not enough: the whole batch at once, below
         }

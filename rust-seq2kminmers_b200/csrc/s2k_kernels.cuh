@@ -3,8 +3,10 @@
 // Pipeline per launch sequence (all on one stream, no host round trip in between):
 //   k_tile_bounds    : per tile, index of the first sequence starting at/after the tile      (tiny)
 //   k_minimizers     : fused HPC keep-mask + in-smem compaction + canonical ntHash (32/31 bit) of every
-//                      l-mer in HPC space + density threshold + ordered append of (hash,start,end,seq)
-//                      records, tile order kept by a decoupled look-back                     (the hot kernel)
+//                      l-mer in HPC space + density threshold + append of (hash,start,end,seq) records to a
+//                      per-CTA region, records of a tile contiguous and ordered            (the hot kernel)
+//   k_tile_scan_a/b, k_finalize : exclusive prefix of per-tile counts -> where every tile's records belong in the
+//                      ordered stream (tile_src), global per-sequence prefixes                        (per tile)
 //   k_read_counts    : per sequence, minimizers feeding the window stage (AVX-512 tail rule) -> item counts,
 //                      exclusive scan -> km_off                                              (n_seqs elements)
 //   k_windows        : one thread per minimizer: k-window hash, canonical min, rev, start/end (~2*rho*d*N elements)
@@ -23,6 +25,7 @@
 //   tail rule            src/nthash_avx512_32.rs:134-138 (last 16 l-mers dropped when S>16 && S%16==0)
 //   window stage         src/lib.rs:157-169 (mix), 231-261 (rolling k-window hash, canonical, rev, start/end/offset)
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #ifdef S2K_EMU            // tests/emu: the same sources compiled by g++ onto host threads (test tier only)
 #include "cuda_emu.h"
@@ -30,7 +33,7 @@
 #define S2K_SHARED static
 #else
 #include <cuda_runtime.h>
-#define S2K_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#define S2K_DYN_SMEM(name) extern __shared__ __align__(1024) uint8_t name[]
 #define S2K_SHARED __shared__
 #endif
 
@@ -86,7 +89,7 @@ constexpr uint64_t FLAG_INCL = 2ull << 62;
 constexpr uint64_t VALMASK   = (1ull << 62) - 1;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
-constexpr uint32_t ERR_SPIN = 1u, ERR_CAP = 2u;
+constexpr uint32_t ERR_SPIN = 1u, ERR_CAP = 2u, ERR_ALIGN = 4u;
 
 struct K1Args {
     const uint8_t  *bases;
@@ -113,6 +116,12 @@ struct K1Args {
 };
 
 struct Smem {
+    // lut and xf sit on 256-byte boundaries of the shared window: their (8-bit) offsets are spliced into the address
+    // with one PRMT instead of an extract + add (smem_splice below); k_minimizers checks the alignment once.
+    alignas(256) uint8_t lut[256];           // raw byte -> 8 * base class
+    alignas(256) uint2 xf[XFN];              // the 16 live entries cover the 32 banks once
+    alignas(128) uint2 x2[XFN];
+    uint2    x4[256];                        // warm-up: (c0,c1,c2,c3) at c0 + 4*c1 + 16*c2 + 64*c3 advances the state by 4 bases
     uint8_t  pre[16];                        // stays ZC8: with l = 255 and owner space shifted 3 bases into the halo the
                                              // word-wise hash stage reads up to 4 bytes below code[0]
     uint8_t  code[XB + WIN + 128];           // 8*class of every kept base, index XB + (kept index in the window)
@@ -128,9 +137,6 @@ struct Smem {
     uint16_t qmap[(XB + WIN) / 64 + 2];      // chunk holding kept base 64*m (coarse inverse of qoff)
     uint2    xy[XYN];
     uint16_t hl[HL];
-    alignas(128) uint2 xf[XFN];              // 128-byte aligned: the 16 live entries cover the 32 banks once
-    alignas(128) uint2 x2[XFN];
-    uint8_t  lut[256];
     uint8_t  sel8[256 * 8];                  // sel8[8*b + r] = position of the r-th set bit of byte b (r < popc(b))
     uint32_t wsum[3][NT / 32];               // warp totals: kept-count scan, hit-count scan of pass 0 / pass 1
     uint32_t hk;
@@ -141,6 +147,7 @@ struct Smem {
     uint16_t dirty[2][DIRTY_MAX];            // double-buffered by tile parity.  bit 15: f1/f2, else startw/shortw
     unsigned long long s0, rec0, rec_lim, cur;   // cur: records this CTA has appended to its region
 };
+static_assert(offsetof(Smem, lut) == 0 && offsetof(Smem, xf) == 256, "k_minimizers derives the lut address from xf's");
 
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint64_t ld_relaxed(const uint64_t *p)
@@ -206,6 +213,36 @@ __device__ __forceinline__ int nth_set_bit(uint32_t w, int r)      // position o
     }
     return pos;
 }
+// ---- shared-memory table look-ups whose byte offset is spliced into the address.
+// A table on a 256-byte boundary of the shared window has an address whose low byte is zero, so
+// PRMT(word, base, 0x765k) = (base & ~0xff) | byte k of word IS the address of entry `byte k`: one instruction where
+// extract + add took two (the compaction does one such look-up per raw base, the hash stage one per l-mer).
+#ifdef S2K_EMU
+typedef const uint8_t *smem_tab_t;
+__device__ __forceinline__ smem_tab_t smem_tab(const void *p) { return reinterpret_cast<const uint8_t *>(p); }
+__device__ __forceinline__ bool smem_tab_ok(smem_tab_t) { return true; }
+__device__ __forceinline__ uint32_t tab_u8(smem_tab_t t, uint32_t w, int k) { return t[(w >> (8 * k)) & 0xffu]; }
+__device__ __forceinline__ uint2 tab_u64(smem_tab_t t, uint32_t w, int k)
+{
+    return *reinterpret_cast<const uint2 *>(t + ((w >> (8 * k)) & 0xffu));
+}
+#else
+typedef uint32_t smem_tab_t;
+__device__ __forceinline__ smem_tab_t smem_tab(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool smem_tab_ok(smem_tab_t t) { return (t & 0xffu) == 0u; }
+__device__ __forceinline__ uint32_t tab_u8(smem_tab_t t, uint32_t w, int k)      // k: a constant after unrolling
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(__byte_perm(w, t, 0x7650u + (uint32_t)k)));
+    return v;
+}
+__device__ __forceinline__ uint2 tab_u64(smem_tab_t t, uint32_t w, int k)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(__byte_perm(w, t, 0x7650u + (uint32_t)k)));
+    return v;
+}
+#endif
 template <bool W31> __device__ __forceinline__ uint32_t rol1(uint32_t x)
 {
     if (W31) return ((x << 1) | (x >> 30)) & 0x7fffffffu;
@@ -225,6 +262,16 @@ template <bool W31> __device__ __forceinline__ uint32_t ror2(uint32_t x)
 {
     if (W31) return (x >> 2) | ((x & 3u) << 29);
     return __funnelshift_r(x, x, 2);
+}
+template <bool W31> __device__ __forceinline__ uint32_t rol4(uint32_t x)
+{
+    if (W31) return ((x << 4) | (x >> 27)) & 0x7fffffffu;
+    return __funnelshift_l(x, x, 4);
+}
+template <bool W31> __device__ __forceinline__ uint32_t ror4(uint32_t x)
+{
+    if (W31) return (x >> 4) | ((x & 15u) << 27);
+    return __funnelshift_r(x, x, 4);
 }
 // Sequence-start flags are sparse: remember which bitmap words were touched so that the next tile clears those
 // instead of zeroing four bitmaps.  More than DIRTY_MAX touched words -> the next tile zeroes everything.
@@ -301,14 +348,19 @@ __device__ __forceinline__ void hash_owners_bytes(const Smem &S, const uint8_t *
 // DENSE: at the usual densities some lane of the warp selects an owner in almost every group of four (2 % of the
 // owners at d = 0.01: 1 - 0.98^128 = 92 %), so a "rare" branch around the bookkeeping would nearly always run; the
 // three predicated instructions per owner are cheaper.  Sparse selections keep the test per group.
+// Multiplier that gathers the four 2-bit classes of a code word (bytes 8*c) into one byte: the high half of
+// w * X4MUL holds c0 | c1 << 2 | c2 << 4 | c3 << 6 in its low byte (no two partial products share a bit and the low
+// half cannot carry: 3 * (2^30 + 2^28 + 2^26 + 2^22 + 2^20 + 2^14) < 2^32).
+constexpr uint32_t X4MUL = (1u << 29) | (1u << 23) | (1u << 17) | (1u << 11);
 template <bool W31, bool DENSE>
-__device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, const uint8_t *cb, int l, uint32_t thr, uint32_t *hs,
-                                                      unsigned long long (&mask)[MW])
+__device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, smem_tab_t xft, const uint8_t *cb, int l, uint32_t thr,
+                                                      uint32_t *hs, unsigned long long (&mask)[MW])
 {
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(cb);
-    const uint8_t *xf = reinterpret_cast<const uint8_t *>(S.xf), *x2 = reinterpret_cast<const uint8_t *>(S.x2);
+    const uint8_t *x2 = reinterpret_cast<const uint8_t *>(S.x2);
     uint32_t fh = 0, rh = 0, seen = 0;
-    {   // warm-up over cb[1-l .. -1]: an odd first base alone (general table), then pairs
+    {   // warm-up over cb[1-l .. -1] (it ends on a word boundary): an odd first base alone (general table), one pair
+        // (two-base table), then whole code words through the four-base table -- 7 steps of 9 instructions for l = 31
         int j = 1 - l;
         if ((l - 1) & 1) {
             const uint32_t c = cb[j];
@@ -316,24 +368,19 @@ __device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, const uint8
             fh = tt.x; rh = tt.y; seen |= c;
             ++j;
         }
-        const int np = (l - 1) >> 1;                       // pairs
-        const int jw = j >> 2;                             // word holding cb[j] (floor: j < 0)
-        const uint32_t sh = (uint32_t)(j & 3) * 8u;
-        uint32_t lo = cw[jw];
-        for (int p = 0; p < np; p += 2) {
-            const uint32_t hi = cw[jw + 1 + (p >> 1)];
-            const uint32_t w = __funnelshift_r(lo, hi, sh);
-            lo = hi;
+        if ((l - 1) & 2) {
+            const uint32_t c1 = cb[j], c2 = cb[j + 1];
+            const uint2 tt = *reinterpret_cast<const uint2 *>(x2 + 4u * c1 + c2);
+            fh = rol2<W31>(fh) ^ tt.x; rh = ror2<W31>(rh) ^ tt.y; seen |= c1 | c2;
+        }
+        const int nw = (l - 1) >> 2;
+#pragma unroll 8
+        for (int wi = -nw; wi < 0; ++wi) {
+            const uint32_t w = cw[wi];
             seen |= w;
-            const uint32_t pi = w * 4u + (w >> 8);         // byte 0: 4*c0+c1, byte 2: 4*c2+c3
-            uint2 tt = *reinterpret_cast<const uint2 *>(x2 + (pi & 0xffu));
-            fh = rol2<W31>(fh) ^ tt.x;
-            rh = ror2<W31>(rh) ^ tt.y;
-            if (p + 1 < np) {
-                tt = *reinterpret_cast<const uint2 *>(x2 + __byte_perm(pi, 0u, 0x4442u));
-                fh = rol2<W31>(fh) ^ tt.x;
-                rh = ror2<W31>(rh) ^ tt.y;
-            }
+            const uint2 tt = S.x4[__umulhi(w, X4MUL) & 0xffu];
+            fh = rol4<W31>(fh) ^ tt.x;
+            rh = ror4<W31>(rh) ^ tt.y;
         }
     }
     const int oq = -((l + 3) >> 2);                        // word of cb[-l] relative to cw, and its byte shift
@@ -348,19 +395,26 @@ __device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, const uint8
         seen |= w_in | w_out;
         const uint32_t i4 = w_out * 4u + w_in;
         uint32_t hv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        {
             uint2 tt;
-            if (g == 0 && k == 0) tt = xy_at(S, ZC8, w_in & 0xffu);     // owner 0: nothing leaves yet
-            else tt = *reinterpret_cast<const uint2 *>(xf + __byte_perm(i4, 0u, 0x4440u + k));
-            fh = rol1<W31>(fh) ^ tt.x;
-            rh = ror1<W31>(rh) ^ tt.y;
-            hv[k] = min(fh, rh);
+            if (g == 0) tt = xy_at(S, ZC8, w_in & 0xffu);           // owner 0: nothing leaves yet
+            else tt = tab_u64(xft, i4, 0);
+            fh = rol1<W31>(fh) ^ tt.x; rh = ror1<W31>(rh) ^ tt.y; hv[0] = min(fh, rh);
+            tt = tab_u64(xft, i4, 1);
+            fh = rol1<W31>(fh) ^ tt.x; rh = ror1<W31>(rh) ^ tt.y; hv[1] = min(fh, rh);
+            tt = tab_u64(xft, i4, 2);
+            fh = rol1<W31>(fh) ^ tt.x; rh = ror1<W31>(rh) ^ tt.y; hv[2] = min(fh, rh);
+            tt = tab_u64(xft, i4, 3);
+            fh = rol1<W31>(fh) ^ tt.x; rh = ror1<W31>(rh) ^ tt.y; hv[3] = min(fh, rh);
         }
         if (DENSE || min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= thr) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
+#if defined(S2K_DIAG) && S2K_DIAG == 3                   // timing experiment only: selected hashes are not stashed
+                if (hv[k] <= thr) { mask[(4 * g + k) >> 6] |= 1ull << ((4 * g + k) & 63); }
+#else
                 if (hv[k] <= thr) { mask[(4 * g + k) >> 6] |= 1ull << ((4 * g + k) & 63); hs[4 * g + k] = hv[k]; }
+#endif
         }
     }
     return seen;
@@ -427,6 +481,12 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     }
     if (tid < XYN) S.xy[tid] = A.xy[tid];
     if (tid < XFN) { S.xf[tid] = A.xf[tid]; S.x2[tid] = A.x2[tid]; }
+    for (int i = tid; i < 256; i += NT) {                   // four warm-up bases at once = two steps of the pair table
+        const uint2 a = A.x2[4 * (i & 3) + ((i >> 2) & 3)], b = A.x2[4 * ((i >> 4) & 3) + (i >> 6)];
+        S.x4[i] = make_uint2(rol2<W31>(a.x) ^ b.x, ror2<W31>(a.y) ^ b.y);
+    }
+    const smem_tab_t xft = smem_tab(S.xf);                 // S.lut lies 256 bytes below: one register for both tables
+    if (tid == 0 && !smem_tab_ok(xft)) atomicOr(A.err, ERR_ALIGN);
     for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
     if (tid < 16) S.pre[tid] = ZC8;
     for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
@@ -575,12 +635,23 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 cp4[v] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
             }
         } else {
+#if defined(S2K_DIAG) && S2K_DIAG == 1                   // timing experiment only (wrong results): conflict-free byte stores
+            uint8_t *cp = S.code + XB + 60 * tid;
+#else
             uint8_t *cp = S.code + XB + q;
+#endif
 #pragma unroll
             for (int b = 0; b < 64; ++b) {
                 const uint32_t kb = (b < 32 ? (klo >> b) : (khi >> (b - 32))) & 1u;
-                if (kb) { *cp = S.lut[__byte_perm(w[b >> 2], 0u, 0x4440u + (b & 3))]; ++cp; }
+#if defined(S2K_DIAG) && S2K_DIAG == 2                   // timing experiment only: no store at all
+                if (kb) { asm volatile("" :: "r"(tab_u8(xft - 256, w[b >> 2], b & 3))); ++cp; }
+#else
+                if (kb) { *cp = (uint8_t)tab_u8(xft - 256, w[b >> 2], b & 3); ++cp; }
+#endif
             }
+#if defined(S2K_DIAG) && S2K_DIAG == 2
+            if (cp == S.code) *cp = 0;
+#endif
         }
         if (tid == 0) S.next[par ^ 1] = t_next;           // the ticket drawn at the top has long arrived
         PHASE(3);
@@ -639,23 +710,13 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // ---- S5 + S6a: rolling canonical ntHash over the owners, CAP per pass; block scan of hit counts
         const uint32_t n_own = wk - (uint32_t)hk;         // kept bases in [T0, T1) (+dlt): each completes one l-mer
         uint32_t tile_min = 0;
+        const int n_pass = n_own > (uint32_t)CAP ? 2 : 1;  // the second pass exists for badly compressing HPC tiles only
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < n_pass; ++pass) {
             unsigned long long mask[MW];
 #pragma unroll
             for (int x = 0; x < MW; ++x) mask[x] = 0ull;
             const int v0 = pass * CAP + CH * tid;
-            if ((uint32_t)(pass * CAP) >= n_own) {         // uniform: nothing left for this pass
-#pragma unroll
-                for (int x = 0; x < MW; ++x) S.hitw[pass][tid][x] = 0ull;
-                S.hitpre[pass][tid] = tile_min;
-                if (tid == NT - 1) {
-#pragma unroll
-                    for (int x = 0; x < MW; ++x) S.hitw[pass][NT][x] = 0ull;
-                    S.hitpre[pass][NT] = tile_min;
-                }
-                continue;
-            }
             if (tid < HT && (uint32_t)v0 < n_own) {
                 const int n_u = min(CH, (int)n_own - v0);
                 // owners invalidated by sequence starts: a start f kills owners [f, f+l-2+d] (+1 if len<=l)
@@ -686,7 +747,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 }
                 if (v0 == 0) invalid[0] |= lowmask64((uint32_t)dlt);   // the pseudo-owners inside the halo
                 const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer; 4-aligned
-                const uint32_t rare = hash_owners_words<W31, DENSE>(S, cb, l, A.thr, hs + v0, mask);
+                const uint32_t rare = hash_owners_words<W31, DENSE>(S, xft, cb, l, A.thr, hs + v0, mask);
                 if (rare & RARE4) {                                // a rare class among the bytes touched: redo via xy
 #pragma unroll
                     for (int x = 0; x < MW; ++x) mask[x] = 0ull;
@@ -739,7 +800,6 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         PHASE(6);
 
         // ---- S7: ordered hit list in shared memory, then one thread per minimizer
-        const int n_pass = n_own > (uint32_t)CAP ? 2 : 1;  // the second pass exists for badly compressing HPC tiles only
         for (uint32_t base = 0; base < tile_min; base += HL) {
             if (base) __syncthreads();                     // previous round has been consumed
 #pragma unroll 1
@@ -798,12 +858,15 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             const uint32_t x = (uint32_t)((int64_t)so - W0);
             const uint32_t qx = S.qoff[x >> 5] + __popc(S.keepw[x >> 5] & lowmask(x & 31));
             const uint32_t v = qx - (uint32_t)hk;
-            const uint32_t pass = v >= (uint32_t)CAP ? 1u : 0u;
-            const uint32_t vv = v - pass * CAP, u = vv / CH, bit = vv - u * CH;
-            uint32_t hb = S.hitpre[pass][u];
+            uint32_t hb = tile_min;                        // a start at the very end of the tile: every hit precedes it
+            if (v < n_own) {
+                const uint32_t pass = v >= (uint32_t)CAP ? 1u : 0u;
+                const uint32_t vv = v - pass * CAP, u = vv / CH, bit = vv - u * CH;
+                hb = S.hitpre[pass][u];
 #pragma unroll
-            for (int x = 0; x < MW; ++x)
-                hb += __popcll(S.hitw[pass][u][x] & lowmask64((uint32_t)max(min((int)bit - 64 * x, 64), 0)));
+                for (int x = 0; x < MW; ++x)
+                    hb += __popcll(S.hitw[pass][u][x] & lowmask64((uint32_t)max(min((int)bit - 64 * x, 64), 0)));
+            }
             A.min_off[i] = hb;
             if (A.hpc_off) A.hpc_off[i] = qx - hk_real;
         }

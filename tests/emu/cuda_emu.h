@@ -241,6 +241,7 @@ static inline unsigned __vcmpne4(unsigned a, unsigned b)
     for (int i = 0; i < 4; ++i) if (((a >> (8 * i)) & 0xff) != ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i);
     return r;
 }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s)
 {
     s &= 31;

@@ -111,6 +111,45 @@ def test_long_sequences_travel_in_pieces_emulated(S, O, emu_ctx, batches):
         emu_ctx.set_transport(0, 0.7)
 
 
+def _tail_rule_cases(rng, l):
+    """Long sequences whose AVX-512 tail rule fires while the last 16 kept bases are reached by l-mers that START far
+    to the left: a no-run stretch followed by a homopolymer tail longer than a piece (the minimizers to drop then
+    start in what would have been the previous piece)."""
+    import numpy as np
+    cases = []
+    for lead, tail, doubled in ((6019, 3200, 5), (6019, 3200, 0), (12000, 9000, 3), (8040, 5000, 0), (20000, 1, 0)):
+        kept = lead + 1
+        lead += (-(kept - l + 1)) % 16                     # S = kept - l + 1 a multiple of 16: the rule fires
+        body = _norun(rng, lead)
+        if doubled:                                        # a few runs of two early on: the first piece (cut after 6000 raw
+            at = np.sort(rng.choice(4000, doubled, replace=False))   # bases) then ends `doubled` kept bases earlier
+            body = np.insert(body, at, body[at])
+        t = np.full(tail, b"ACGT"[(b"ACGT".index(bytes([body[-1]])) + 1) % 4], np.uint8)
+        cases.append(np.concatenate([body, t]))
+    return cases
+
+
+def test_tail_rule_minimizers_belong_to_the_last_piece_emulated(S, O, emu_ctx, batches):
+    """the minimizers the AVX-512 tail rule drops END in the last 16 kept bases but may START a
+    whole piece earlier (homopolymer tail).  The piece plan keeps every such start inside the last piece."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    l = 21
+    for seq in _tail_rule_cases(rng, l):
+        kept = 1 + int(np.count_nonzero(seq[1:] != seq[:-1]))
+        assert (kept - l + 1) % 16 == 0 and kept - l + 1 > 16
+        bases, so = batches.pack([batches.seq(500), seq, batches.seq(300)])
+        emu_ctx.set_slab_bytes(6000)
+        try:
+            for k, d in ((2, 1.0), (3, 0.3)):
+                emu_ctx.set_transport(3, 0.5)
+                got = emu_ctx.run(bases, so, l, k, d, S.HashMode.HpcSimd, S.HashVariant(0), want_minimizers=True)
+                assert_batch_matches_oracle(O, got, bases, so, l, k, d, int(S.HashMode.HpcSimd), 0)
+        finally:
+            emu_ctx.set_slab_bytes(0)
+            emu_ctx.set_transport(0, 0.7)
+
+
 def _pack2_numpy(bases):
     """Independent restatement of the packed layout: base i in bits 2*(i%4) of byte i/4, code (ascii>>1)&3."""
     import numpy as np

@@ -6,6 +6,6 @@ for v in "$@"; do
   for rep in 1 2; do
     python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e 2>/dev/null | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('[$v]', round(d['value'],1), 'Gbp/s  k_minimizers', round(d['roofline']['ms_per_step_in_kernel'],3), 'ms')"
+d=json.loads(sys.stdin.read()); print('[$v]', round(d['value'],1), 'Gbp/s  k_minimizers', round(d['roofline']['ms_per_step_in_kernel'],3), 'ms  items', d['items_per_step'])"
   done
-done
+done 2>&1 | tee -a gpurun_out/ab.txt
