@@ -44,7 +44,7 @@ namespace s2k {
 #define S2K_NT 256
 #endif
 constexpr int NT    = S2K_NT;       // threads per CTA
-constexpr int RAWPT = 64;           // raw bases per thread in the keep/compaction phase
+constexpr int RAWPT = 64;           // raw bases per thread in the keep/compaction phase: four pieces of 16
 constexpr int WIN   = NT * RAWPT;   // raw bases staged per tile (left halo + tile)
 constexpr int NCHUNK = WIN / 32;    // 32-base chunks per window
 #ifndef S2K_CH
@@ -521,23 +521,28 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const bool last_tile = (uint64_t)T1 == A.n_bases;
         const uint32_t lb = S.nlb[par][0], ub = S.nlb[par][1];
 
-        // ---- S3a: this thread's 64 raw bases, global -> registers (issued first: the latency overlaps S2)
-        const int64_t g0 = W0 + RAWPT * tid;
+        // ---- S3a: this thread's 64 raw bases, global -> registers (issued first: the latency overlaps S2).
+        // A warp covers 2048 consecutive bases of the window in four rounds of 32 PIECES of 16 bases: in round j lane L
+        // holds piece 32*j + L, so a round's loads are one contiguous 512-byte row, and the kept bases of neighbouring
+        // lanes land about 12 bytes = 3 words apart in S.code: the compaction's byte stores of a round fall into
+        // different banks (64 consecutive bases per thread put the lanes 12 words apart: 4-way conflicts).
+        const int xw = 2048 * warp + 16 * lane;            // window offset of this thread's piece of round 0
+        const bool full = W0 >= 0 && W0 + (int64_t)WIN <= (int64_t)A.n_bases;      // uniform: the whole window is readable
         uint32_t w[16];
-        if (g0 >= 0 && g0 + RAWPT <= (int64_t)A.n_bases) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(A.bases + g0);
+        if (full) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.bases + W0 + xw);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const uint4 x = __ldg(src + v);
-                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            for (int j = 0; j < 4; ++j) {
+                const uint4 x = __ldg(src + 32 * j);
+                w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
             }
         } else {
 #pragma unroll
             for (int v = 0; v < 16; ++v) {
                 uint32_t x = 0;
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t gg = g0 + 4 * v + j;
-                    if (gg >= 0 && gg < (int64_t)A.n_bases) x |= (uint32_t)A.bases[gg] << (8 * j);
+                for (int b = 0; b < 4; ++b) {
+                    const int64_t gg = W0 + xw + 512 * (v >> 2) + 4 * (v & 3) + b;
+                    if (gg >= 0 && gg < (int64_t)A.n_bases) x |= (uint32_t)A.bases[gg] << (8 * b);
                 }
                 w[v] = x;
             }
@@ -568,90 +573,107 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         __syncthreads();
         PHASE(1);
 
-        // ---- S3b: keep mask, block scan of kept counts
-        uint32_t klo, khi;
+        // ---- S3b: keep masks (16 bits per piece), block scan of kept counts
+        uint32_t k16[4], st16[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t sw = S.startw[64 * warp + 16 * j + (lane >> 1)];
+            st16[j] = (lane & 1) ? (sw >> 16) : (sw & 0xffffu);
+        }
         if (HPC) {
             // keep bit = byte differs from the byte before it.  Per word: PRMT lines the previous bytes up, XOR, the
             // classic "byte is non-zero" carry trick leaves bit 7 of each byte, one multiply gathers the four bits into
             // the top nibble and a funnel shift appends it -- words are visited from high to low so that base 0 ends up
-            // in bit 0.
-            uint32_t prevw = __shfl_up_sync(0xffffffffu, w[15], 1);
-            if (lane == 0) prevw = ((g0 > 0 && g0 <= (int64_t)A.n_bases) ? (uint32_t)A.bases[g0 - 1] : 0u) << 24;
-            uint32_t kk[2] = {0u, 0u};
+            // in bit 0.  The byte before a piece is the last byte of the lane below (lane 0: lane 31 of the round before;
+            // round 0: the last byte of the warp before, from global memory).
 #pragma unroll
-            for (int i = 15; i >= 0; --i) {
-                const uint32_t x = w[i] ^ __byte_perm(i ? w[i - 1] : prevw, w[i], 0x6543u);
-                const uint32_t nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
-                kk[i >> 3] = __funnelshift_l(nz * 0x00204081u, kk[i >> 3], 4);
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t send = (j > 0 && lane == 31) ? w[4 * j - 1] : w[4 * j + 3];
+                uint32_t prevw = __shfl_sync(0xffffffffu, send, (lane + 31) & 31);
+                if (j == 0 && lane == 0) {
+                    const int64_t g = W0 + xw;
+                    prevw = ((g > 0 && g <= (int64_t)A.n_bases) ? (uint32_t)A.bases[g - 1] : 0u) << 24;
+                }
+                uint32_t kk = 0u;
+#pragma unroll
+                for (int i = 3; i >= 0; --i) {
+                    const uint32_t x = w[4 * j + i] ^ __byte_perm(i ? w[4 * j + i - 1] : prevw, w[4 * j + i], 0x6543u);
+                    const uint32_t nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+                    kk = __funnelshift_l(nz * 0x00204081u, kk, 4);
+                }
+                k16[j] = kk | st16[j];
             }
-            klo = kk[0] | S.startw[2 * tid];
-            khi = kk[1] | S.startw[2 * tid + 1];
         } else {
-            klo = khi = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) k16[j] = 0xffffu;
         }
-        {
-            unsigned long long vmask = ~0ull;
-            if (g0 < 0) vmask = (g0 <= -64) ? 0ull : (~0ull << (int)(-g0));
-            const int64_t rem = T1 - g0;
-            if (rem <= 0) vmask = 0ull; else if (rem < 64) vmask &= (1ull << (int)rem) - 1ull;
-            klo &= (uint32_t)vmask; khi &= (uint32_t)(vmask >> 32);
+        const int x_hi = (int)(T1 - W0);                   // window offsets [x_lo, x_hi) hold the bases of [max(W0,0), T1)
+        if (!full || x_hi < WIN) {
+            const int x_lo = W0 < 0 ? (int)min((int64_t)WIN, -W0) : 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x0 = xw + 512 * j;
+                const int a = min(max(x_lo - x0, 0), 16), e = min(max(x_hi - x0, 0), 16);
+                k16[j] &= e > a ? (lowmask((uint32_t)e) & ~lowmask((uint32_t)a)) : 0u;
+            }
         }
-        const uint32_t clo = __popc(klo);
-        // The thread that holds the halo/tile boundary sits in warp 0 (halo <= 512 raw bases = 8 threads): its prefix
-        // needs no warp totals, so the kept count of the halo is published before the scan's only barrier.
-        const uint32_t cnt_kept = clo + __popc(khi);
-        const uint32_t incl_kept = warp_incl_scan(cnt_kept, lane);
-        if (lane == 31) S.wsum[0][warp] = incl_kept;
-        if (tid == (int)(A.halo >> 6)) S.hk = incl_kept - cnt_kept + (((A.halo >> 5) & 1u) ? clo : 0u);
+        // One warp scan per pair of rounds (counts of a round sum to at most 512: 16-bit fields), then the rounds'
+        // totals: kept bases before piece (j, lane) = before the warp + rounds below j + lanes below in round j.
+        const uint32_t c0 = __popc(k16[0]), c1 = __popc(k16[1]), c2 = __popc(k16[2]), c3 = __popc(k16[3]);
+        const uint32_t i01 = warp_incl_scan(c0 | (c1 << 16), lane), i23 = warp_incl_scan(c2 | (c3 << 16), lane);
+        const uint32_t t01 = __shfl_sync(0xffffffffu, i01, 31), t23 = __shfl_sync(0xffffffffu, i23, 31);
+        uint32_t qj[4];
+        qj[0] = (i01 & 0xffffu) - c0;
+        qj[1] = (t01 & 0xffffu) + (i01 >> 16) - c1;
+        qj[2] = (t01 & 0xffffu) + (t01 >> 16) + (i23 & 0xffffu) - c2;
+        qj[3] = (t01 & 0xffffu) + (t01 >> 16) + (t23 & 0xffffu) + (i23 >> 16) - c3;
+        if (lane == 31) S.wsum[0][warp] = (t01 & 0xffffu) + (t01 >> 16) + (t23 & 0xffffu) + (t23 >> 16);
+        // The piece at the halo/tile boundary sits in warp 0 (halo <= 512 raw bases): its prefix needs no warp totals,
+        // so the kept count of the halo is published before the scan's only barrier.
+        if (warp == 0 && lane == (int)((A.halo >> 4) & 31u)) S.hk = (A.halo >> 9) ? qj[1] : qj[0];
         __syncthreads();
-        uint32_t q = incl_kept - cnt_kept, wk = 0;
+        uint32_t qw = 0, wk = 0;
 #pragma unroll
         for (int i = 0; i < NT / 32; ++i) {
             const uint32_t sw = S.wsum[0][i];
-            if (i < warp) q += sw;
+            if (i < warp) qw += sw;
             wk += sw;
         }
-        S.keepw[2 * tid] = klo; S.keepw[2 * tid + 1] = khi;
-        S.qoff[2 * tid] = q; S.qoff[2 * tid + 1] = q + clo;
+        {
+            uint16_t *kw16 = reinterpret_cast<uint16_t *>(S.keepw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                qj[j] += qw;
+                const int pc = 128 * warp + 32 * j + lane;  // piece index in the window; chunk = pc >> 1
+                kw16[pc] = (uint16_t)k16[j];
+                if (!(lane & 1)) S.qoff[pc >> 1] = qj[j];
+                const uint32_t m = (qj[j] + 63u) & ~63u;    // a piece holds at most 16 kept bases: at most one multiple of 64
+                if (m < qj[j] + __popc(k16[j])) S.qmap[m >> 6] = (uint16_t)(pc >> 1);
+            }
+        }
         if (tid == NT - 1) { S.qoff[NCHUNK] = wk; S.keepw[NCHUNK] = 0; }
-        for (uint32_t m = (q + 63u) & ~63u; m < q + clo + __popc(khi); m += 64)
-            S.qmap[m >> 6] = (uint16_t)(m < q + clo ? 2 * tid : 2 * tid + 1);
 
         PHASE(2);
         // ---- S4: compaction (predicated byte stores in HPC order)
-        if (!HPC && (klo & khi) == 0xffffffffu && ((XB + q) & 15u) == 0) {
-            // every base kept (no HPC): byte stores would advance at a 64-byte lane stride = 16-way bank conflicts.
-            // Pack the 64 classes and store four 16-byte vectors instead.
-            uint4 *cp4 = reinterpret_cast<uint4 *>(S.code + XB + q);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+        for (int j = 0; j < 4; ++j) {
+            if (!HPC && k16[j] == 0xffffu && ((XB + qj[j]) & 15u) == 0) {
+                // every base kept (no HPC): the 16 classes of the piece as one 16-byte store
                 uint32_t o4[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint32_t x = w[4 * v + i];
+                    const uint32_t x = w[4 * j + i];
                     o4[i] = (uint32_t)S.lut[x & 0xffu] | ((uint32_t)S.lut[(x >> 8) & 0xffu] << 8) |
                             ((uint32_t)S.lut[(x >> 16) & 0xffu] << 16) | ((uint32_t)S.lut[x >> 24] << 24);
                 }
-                cp4[v] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-            }
-        } else {
-#if defined(S2K_DIAG) && S2K_DIAG == 1                   // timing experiment only (wrong results): conflict-free byte stores
-            uint8_t *cp = S.code + XB + 60 * tid;
-#else
-            uint8_t *cp = S.code + XB + q;
-#endif
+                *reinterpret_cast<uint4 *>(S.code + XB + qj[j]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            } else {
+                uint8_t *cp = S.code + XB + qj[j];
 #pragma unroll
-            for (int b = 0; b < 64; ++b) {
-                const uint32_t kb = (b < 32 ? (klo >> b) : (khi >> (b - 32))) & 1u;
-#if defined(S2K_DIAG) && S2K_DIAG == 2                   // timing experiment only: no store at all
-                if (kb) { asm volatile("" :: "r"(tab_u8(xft - 256, w[b >> 2], b & 3))); ++cp; }
-#else
-                if (kb) { *cp = (uint8_t)tab_u8(xft - 256, w[b >> 2], b & 3); ++cp; }
-#endif
+                for (int b = 0; b < 16; ++b) {
+                    if ((k16[j] >> b) & 1u) { *cp = (uint8_t)tab_u8(xft - 256, w[4 * j + (b >> 2)], b & 3); ++cp; }
+                }
             }
-#if defined(S2K_DIAG) && S2K_DIAG == 2
-            if (cp == S.code) *cp = 0;
-#endif
         }
         if (tid == 0) S.next[par ^ 1] = t_next;           // the ticket drawn at the top has long arrived
         PHASE(3);
@@ -660,15 +682,19 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const uint32_t hk_real = S.hk;
         const int dlt = (int)((hk_real - (uint32_t)d) & 3u);
         const int hk = (int)hk_real - dlt;
-        {   // sequence starts among this thread's kept bases -> owner-space flags (rare)
-            const unsigned long long keep = ((unsigned long long)khi << 32) | klo;
-            unsigned long long sw = (((unsigned long long)S.startw[2 * tid + 1] << 32) | S.startw[2 * tid]) & keep;
-            const unsigned long long sh2 = ((unsigned long long)S.shortw[2 * tid + 1] << 32) | S.shortw[2 * tid];
-            while (sw) {
-                const int b = __ffsll((long long)sw) - 1;
-                sw &= sw - 1;
-                const int oo = (int)q + __popcll(keep & lowmask64(b)) - hk + XB;
-                if (oo >= 0) flag_owner(S, par, oo, (sh2 >> b) & 1ull);
+        if (st16[0] | st16[1] | st16[2] | st16[3]) {       // sequence starts among this thread's kept bases -> owner-space flags
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t sw = st16[j] & k16[j];
+                if (sw) {
+                    const uint32_t sh2 = S.shortw[64 * warp + 16 * j + (lane >> 1)] >> (16 * (lane & 1));
+                    while (sw) {
+                        const int b = __ffs((int)sw) - 1;
+                        sw &= sw - 1;
+                        const int oo = (int)qj[j] + __popc(k16[j] & lowmask((uint32_t)b)) - hk + XB;
+                        if (oo >= 0) flag_owner(S, par, oo, (sh2 >> b) & 1u);
+                    }
+                }
             }
         }
         // ---- S4b: not enough context in the halo -> walk back through the sequence (rare: long homopolymers)
