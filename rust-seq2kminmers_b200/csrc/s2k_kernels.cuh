@@ -62,6 +62,8 @@ constexpr int CAP   = HT * CH;      // owners hashed per pass (a second pass cov
 static_assert(CH % 4 == 0 && ((CH / 4) & 1) == 1 && CH <= 128 && HT <= NT && 2 * CAP >= WIN, "hash geometry");
 constexpr int XB    = 256;          // capacity of the left context, in kept (HPC) bases
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
+constexpr int PKW   = (XB + WIN) / 16 + 8;   // words of the packed code array (a multiple of 4)
+constexpr int PK_LMAX = 33;                  // packed tiles serve l <= 33: the warm-up reads 32 codes from two registers
 #ifndef S2K_HL
 #define S2K_HL 1024
 #endif
@@ -120,9 +122,13 @@ struct Smem {
     // with one PRMT instead of an extract + add (smem_splice below); k_minimizers checks the alignment once.
     alignas(256) uint8_t lut[256];           // raw byte -> 8 * base class
     alignas(256) uint2 xf[XFN];              // the 16 live entries cover the 32 banks once
+    alignas(256) uint8_t lut2[256];          // raw byte -> 2-bit class (A C G T = 0..3), 0x80 for the two rare classes
     alignas(128) uint2 x2[XFN];
     uint2    x4[256];                        // warm-up: (c0,c1,c2,c3) at c0 + 4*c1 + 16*c2 + 64*c3 advances the state by 4 bases
-    uint8_t  pre[16];                        // stays ZC8: with l = 255 and owner space shifted 3 bases into the halo the
+    uint2    xrm[64];                        // packed warm-up: what the 0..3 oldest codes of its first byte added (see hash_owners_packed)
+    alignas(16) uint32_t pk[PKW];            // packed tiles: 2-bit class of every kept base, 16 per word, same index space as code[]
+    uint32_t rare;                           // a thread met a rare class while packing: the tile is redone byte-wise
+    alignas(16) uint8_t pre[16];             // stays ZC8: with l = 255 and owner space shifted 3 bases into the halo the
                                              // word-wise hash stage reads up to 4 bytes below code[0]
     uint8_t  code[XB + WIN + 128];           // 8*class of every kept base, index XB + (kept index in the window)
     unsigned long long hitw[2][NT + 1][MW];  // per pass, per thread: selected owners (bit i = owner CH*t + i)
@@ -147,7 +153,9 @@ struct Smem {
     uint16_t dirty[2][DIRTY_MAX];            // double-buffered by tile parity.  bit 15: f1/f2, else startw/shortw
     unsigned long long s0, rec0, rec_lim, cur;   // cur: records this CTA has appended to its region
 };
-static_assert(offsetof(Smem, lut) == 0 && offsetof(Smem, xf) == 256, "k_minimizers derives the lut address from xf's");
+static_assert(offsetof(Smem, lut) == 0 && offsetof(Smem, xf) == 256 && offsetof(Smem, lut2) == 512,
+              "k_minimizers derives the lut addresses from xf's");
+static_assert(offsetof(Smem, code) % 16 == 0 && offsetof(Smem, pk) % 16 == 0, "vector stores into code[] and pk[]");
 
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint64_t ld_relaxed(const uint64_t *p)
@@ -262,6 +270,17 @@ template <bool W31> __device__ __forceinline__ uint32_t ror2(uint32_t x)
 {
     if (W31) return (x >> 2) | ((x & 3u) << 29);
     return __funnelshift_r(x, x, 2);
+}
+// a * b + c kept on the multiply-add pipe (IMAD), away from the integer ALU
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+#ifdef S2K_EMU
+    return a * b + c;
+#else
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#endif
 }
 template <bool W31> __device__ __forceinline__ uint32_t rol4(uint32_t x)
 {
@@ -410,14 +429,117 @@ __device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, smem_tab_t 
         if (DENSE || min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= thr) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-#if defined(S2K_DIAG) && S2K_DIAG == 3                   // timing experiment only: selected hashes are not stashed
-                if (hv[k] <= thr) { mask[(4 * g + k) >> 6] |= 1ull << ((4 * g + k) & 63); }
-#else
                 if (hv[k] <= thr) { mask[(4 * g + k) >> 6] |= 1ull << ((4 * g + k) & 63); hs[4 * g + k] = hv[k]; }
-#endif
         }
     }
     return seen;
+}
+
+// hash_owners_packed: the same CH owners from the PACKED code array (2 bits per kept base; tiles without rare classes
+// and without a walk-back).  E = index (code[] space) of the last base of owner 0's l-mer.  Seven consecutive words of
+// the array, funnel-shifted once, hold codes E-32 .. E+63 in registers: two words of warm-up context and the entering
+// codes of all owners; five more give the leaving codes.  Per 16 owners the (out,in) pairs are interleaved into
+// nibbles (X: even owners, Y: odd owners; two LOP3 + two shifts) and spread into four words of table offsets
+// 8*(4*out+in), one per byte -- 12 instructions where the byte path spends 20 (two loads, a funnel shift, an IMAD and a
+// rare-class OR per group of four).  Warm-up: the l-1 codes before owner 0 are rounded UP to whole bytes, each byte is
+// one look-up in the four-base table (a packed byte IS its index), and what the 0..3 surplus codes of the oldest byte
+// added is taken out again with one look-up in xrm (the hash is XOR-linear in the bases).
+template <bool W31, bool DENSE>
+__device__ __forceinline__ void hash_owners_packed(const Smem &S, smem_tab_t xft, int E, int l, uint32_t thr, uint32_t *hs,
+                                                   unsigned long long (&mask)[MW])
+{
+    constexpr int NG = (CH + 15) / 16;
+    uint32_t mw[2 * MW];                                   // the hit mask as 32-bit words
+#pragma unroll
+    for (int x = 0; x < 2 * MW; ++x) mw[x] = 0u;
+    uint32_t R[NG + 2];                                    // R[0], R[1]: codes E-32 .. E-1; R[2 + g]: codes E+16g ..
+    {
+        const int e0 = E - 32;
+        const uint32_t *pw = S.pk + (e0 >> 4);
+        const uint32_t sh = 2u * (uint32_t)(e0 & 15);
+        uint32_t a = pw[0];
+#pragma unroll
+        for (int i = 0; i < NG + 2; ++i) {
+            const uint32_t b = pw[i + 1];
+            R[i] = __funnelshift_r(a, b, sh);
+            a = b;
+        }
+    }
+    uint32_t fh = 0, rh = 0;
+    {   // warm-up: bytes nb-1 .. 0 counted back from code E-1 (static positions), oldest first
+        const int n = l - 1, nb = (n + 3) >> 2, sur = 4 * nb - n;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            if (k < nb) {
+                const uint32_t by = ((k < 4 ? R[1] : R[0]) >> (8 * (3 - (k & 3)))) & 0xffu;
+                const uint2 tt = S.x4[by];
+                fh = rol4<W31>(fh) ^ tt.x;
+                rh = ror4<W31>(rh) ^ tt.y;
+            }
+        }
+        if (sur) {
+            const uint32_t ob = ((nb > 4 ? R[0] : R[1]) >> (8 * ((8 - nb) & 3))) & ((1u << (2 * sur)) - 1u);
+            const uint2 tt = S.xrm[ob];
+            fh ^= tt.x; rh ^= tt.y;
+        }
+    }
+    uint32_t O[NG + 1];
+    {
+        const int o0 = E - l;
+        const uint32_t *pw = S.pk + (o0 >> 4);
+        const uint32_t sh = 2u * (uint32_t)(o0 & 15);
+        uint32_t a = pw[0];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            const uint32_t b = pw[i + 1];
+            O[i] = __funnelshift_r(a, b, sh);
+            a = b;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const uint32_t in = R[2 + g], out = O[g];
+        const uint32_t X = (in & 0x33333333u) | ((out << 2) & 0xccccccccu);        // nibble n: owner 2n   (4*out + in)
+        const uint32_t Y = ((in >> 2) & 0x33333333u) | (out & 0xccccccccu);        // nibble n: owner 2n+1
+        const uint32_t Wt[4] = {(X << 3) & 0x78787878u, (Y << 3) & 0x78787878u,    // byte r: owner 4r + t
+                                (X >> 1) & 0x78787878u, (Y >> 1) & 0x78787878u};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (16 * g + 4 * r >= CH) break;
+            uint32_t hv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint2 tt;
+                if (g == 0 && r == 0 && t == 0) tt = xy_at(S, ZC8, (in & 3u) << 3);   // owner 0: nothing leaves yet
+                else tt = tab_u64(xft, Wt[t], r);
+                fh = rol1<W31>(fh) ^ tt.x; rh = ror1<W31>(rh) ^ tt.y; hv[t] = min(fh, rh);
+            }
+            if (DENSE || min(min(hv[0], hv[1]), min(hv[2], hv[3])) <= thr) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int i = 16 * g + 4 * r + t;
+                    if (hv[t] <= thr) { mw[i >> 5] = mad_u32(1u << (i & 31), 1u, mw[i >> 5]); hs[i] = hv[t]; }   // "|=" on the multiply-add pipe
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < MW; ++x) mask[x] |= (unsigned long long)mw[2 * x] | ((unsigned long long)mw[2 * x + 1] << 32);
+}
+
+// Rotations by a run-time amount within w = 32 or 31 bits (table construction only).
+template <bool W31> __device__ __forceinline__ uint32_t rolv(uint32_t x, uint32_t s)
+{
+    const uint32_t w = W31 ? 31u : 32u;
+    s %= w;
+    if (s == 0) return x;
+    return ((x << s) | (x >> (w - s))) & (W31 ? 0x7fffffffu : 0xffffffffu);
+}
+template <bool W31> __device__ __forceinline__ uint32_t rorv(uint32_t x, uint32_t s)
+{
+    const uint32_t w = W31 ? 31u : 32u;
+    s %= w;
+    return rolv<W31>(x, w - s);
 }
 
 // ------------------------------------------------------------------------------------------------ tile bounds
@@ -464,6 +586,88 @@ __device__ unsigned long long g_phase[16];
 #define PHASE(i)
 #define PHASE_FLUSH
 #endif
+// S3a of k_minimizers: this thread's four pieces of 16 raw bases (piece 32*j + lane of its warp's 2048 bases).
+__device__ __forceinline__ void load_pieces(const K1Args &A, int64_t W0, int xw, bool full, uint32_t (&w)[16])
+{
+    if (full) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.bases + W0 + xw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 x = __ldg(src + 32 * j);
+            w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+            uint32_t x = 0;
+            for (int b = 0; b < 4; ++b) {
+                const int64_t gg = W0 + xw + 512 * (v >> 2) + 4 * (v & 3) + b;
+                if (gg >= 0 && gg < (int64_t)A.n_bases) x |= (uint32_t)A.bases[gg] << (8 * b);
+            }
+            w[v] = x;
+        }
+    }
+}
+// S4, byte form: class bytes (8 * class) of the kept bases to S.code, predicated byte stores in HPC order.
+template <bool HPC>
+__device__ __forceinline__ void compact_bytes(Smem &S, smem_tab_t xft, const uint32_t (&w)[16], const uint32_t (&k16)[4],
+                                              const uint32_t (&qj)[4])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (!HPC && k16[j] == 0xffffu && ((XB + qj[j]) & 15u) == 0) {
+            // every base kept (no HPC): the 16 classes of the piece as one 16-byte store
+            uint32_t o4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t x = w[4 * j + i];
+                o4[i] = (uint32_t)S.lut[x & 0xffu] | ((uint32_t)S.lut[(x >> 8) & 0xffu] << 8) |
+                        ((uint32_t)S.lut[(x >> 16) & 0xffu] << 16) | ((uint32_t)S.lut[x >> 24] << 24);
+            }
+            *reinterpret_cast<uint4 *>(S.code + XB + qj[j]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+            uint8_t *cp = S.code + XB + qj[j];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                if ((k16[j] >> b) & 1u) { *cp = (uint8_t)tab_u8(xft - 256, w[4 * j + (b >> 2)], b & 3); ++cp; }
+            }
+        }
+    }
+}
+// S4, packed form: the 2-bit classes of a piece's kept bases are gathered in ONE register (bases visited from last to
+// first, acc = 4*acc + class: the first kept base ends up in the low bits) and OR-ed into the packed array with at most
+// two shared-memory atomics per piece -- 8 per thread where the byte form issues 64 conflicting byte stores.
+// Returns the OR of the look-ups: bit 7 set = a rare class was met (the caller redoes the tile in byte form).
+__device__ __forceinline__ uint32_t compact_packed(Smem &S, smem_tab_t xft, const uint32_t (&w)[16], const uint32_t (&k16)[4],
+                                                   const uint32_t (&qj)[4])
+{
+    smem_tab_t t2 = xft + 256;                             // S.lut2
+#ifndef S2K_EMU
+    asm volatile("" : "+r"(t2));                           // one register for the whole loop (else re-derived per base)
+#endif
+    uint32_t seen = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // acc gathers the classes; sum adds the look-ups up on the multiply-add pipe (the integer ALU is the busiest
+        // unit of this kernel): 16 classes sum to at most 48, a rare class (0x80) lifts the sum to 128 or more
+        uint32_t acc = 0, sum = 0;
+#pragma unroll
+        for (int b = 15; b >= 0; --b) {
+            if ((k16[j] >> b) & 1u) {
+                const uint32_t v = tab_u8(t2, w[4 * j + (b >> 2)], b & 3);
+                acc = acc * 4u + v;
+                sum = mad_u32(v, 1u, sum);
+            }
+        }
+        seen |= sum;
+        const uint32_t p0 = (uint32_t)XB + qj[j], sh = 2u * (p0 & 15u);
+        const uint32_t lo = acc << sh, hi = __funnelshift_l(acc, 0u, sh);
+        if (lo) atomicOr(&S.pk[p0 >> 4], lo);
+        if (hi) atomicOr(&S.pk[(p0 >> 4) + 1], hi);
+    }
+    return seen >= 128u ? 0x80u : 0u;
+}
+
 template <bool HPC, bool W31, bool DENSE>
 __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_constant__ K1Args A)
 {
@@ -485,7 +689,20 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const uint2 a = A.x2[4 * (i & 3) + ((i >> 2) & 3)], b = A.x2[4 * ((i >> 4) & 3) + (i >> 6)];
         S.x4[i] = make_uint2(rol2<W31>(a.x) ^ b.x, ror2<W31>(a.y) ^ b.y);
     }
-    const smem_tab_t xft = smem_tab(S.xf);                 // S.lut lies 256 bytes below: one register for both tables
+    for (int i = tid; i < 256; i += NT) { const uint32_t c = A.cls_lut[i]; S.lut2[i] = (uint8_t)(c < (uint32_t)ZC8 ? c >> 3 : 0x80u); }
+    if (tid < 64) {                                        // xrm: see hash_owners_packed (A.xy[32 + c] = (h[c], rol(rc[c], l-1)))
+        const int n = (int)A.l - 1, nb = (n + 3) >> 2, sur = 4 * nb - n;
+        uint2 e = make_uint2(0u, 0u);
+        for (int i = 0; i < sur; ++i) {
+            const uint2 hc = A.xy[32 + ((tid >> (2 * i)) & 3)];
+            e.x ^= rolv<W31>(hc.x, (uint32_t)(4 * nb - 1 - i));
+            e.y ^= rorv<W31>(hc.y, (uint32_t)(4 * nb - 1 - i));
+        }
+        S.xrm[tid] = e;
+    }
+    for (int i = tid; i < PKW; i += NT) S.pk[i] = 0u;
+    if (tid == 0) S.rare = 0u;
+    const smem_tab_t xft = smem_tab(S.xf);                 // S.lut lies 256 bytes below, S.lut2 256 above: one register
     if (tid == 0 && !smem_tab_ok(xft)) atomicOr(A.err, ERR_ALIGN);
     for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
     if (tid < 16) S.pre[tid] = ZC8;
@@ -529,24 +746,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const int xw = 2048 * warp + 16 * lane;            // window offset of this thread's piece of round 0
         const bool full = W0 >= 0 && W0 + (int64_t)WIN <= (int64_t)A.n_bases;      // uniform: the whole window is readable
         uint32_t w[16];
-        if (full) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(A.bases + W0 + xw);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint4 x = __ldg(src + 32 * j);
-                w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < 16; ++v) {
-                uint32_t x = 0;
-                for (int b = 0; b < 4; ++b) {
-                    const int64_t gg = W0 + xw + 512 * (v >> 2) + 4 * (v & 3) + b;
-                    if (gg >= 0 && gg < (int64_t)A.n_bases) x |= (uint32_t)A.bases[gg] << (8 * b);
-                }
-                w[v] = x;
-            }
-        }
+        load_pieces(A, W0, xw, full, w);
 
         // ---- S2: sequence starts inside the tile (and the start of the sequence containing T0, if in the window)
         for (uint32_t i = lb + tid; i < ub; i += NT) {
@@ -654,32 +854,21 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         if (tid == NT - 1) { S.qoff[NCHUNK] = wk; S.keepw[NCHUNK] = 0; }
 
         PHASE(2);
-        // ---- S4: compaction (predicated byte stores in HPC order)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (!HPC && k16[j] == 0xffffu && ((XB + qj[j]) & 15u) == 0) {
-                // every base kept (no HPC): the 16 classes of the piece as one 16-byte store
-                uint32_t o4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t x = w[4 * j + i];
-                    o4[i] = (uint32_t)S.lut[x & 0xffu] | ((uint32_t)S.lut[(x >> 8) & 0xffu] << 8) |
-                            ((uint32_t)S.lut[(x >> 16) & 0xffu] << 16) | ((uint32_t)S.lut[x >> 24] << 24);
-                }
-                *reinterpret_cast<uint4 *>(S.code + XB + qj[j]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-            } else {
-                uint8_t *cp = S.code + XB + qj[j];
-#pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    if ((k16[j] >> b) & 1u) { *cp = (uint8_t)tab_u8(xft - 256, w[4 * j + (b >> 2)], b & 3); ++cp; }
-                }
-            }
+        // ---- S4: compaction.  Packed form (2 bits per kept base, register-gathered) unless the halo is too short for
+        // the left context (walk-back below) or l is beyond its warm-up; a rare class met on the way turns the tile back
+        // to the byte form after the barrier.
+        const uint32_t hk_real = S.hk;
+        const bool need_walk = HPC && (int64_t)S.s0 < W0 && hk_real < A.need;
+        const bool try_packed = !need_walk && l <= PK_LMAX;
+        if (try_packed) {
+            if (compact_packed(S, xft, w, k16, qj) & 0x80u) S.rare = 1u;
+        } else {
+            compact_bytes<HPC>(S, xft, w, k16, qj);
         }
         if (tid == 0) S.next[par ^ 1] = t_next;           // the ticket drawn at the top has long arrived
         PHASE(3);
         // Owner space starts up to 3 kept bases inside the halo (those pseudo-owners are masked out below) so that
         // every thread's class bytes begin on a word boundary of S.code: the hash stage reads them as words.
-        const uint32_t hk_real = S.hk;
         const int dlt = (int)((hk_real - (uint32_t)d) & 3u);
         const int hk = (int)hk_real - dlt;
         if (st16[0] | st16[1] | st16[2] | st16[3]) {       // sequence starts among this thread's kept bases -> owner-space flags
@@ -698,7 +887,6 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             }
         }
         // ---- S4b: not enough context in the halo -> walk back through the sequence (rare: long homopolymers)
-        const bool need_walk = HPC && (int64_t)S.s0 < W0 && hk_real < A.need;
         if (need_walk && warp == 0) {
             uint32_t remaining = A.need - hk_real, taken = 0;
             const int64_t s0 = (int64_t)S.s0;
@@ -724,6 +912,12 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             }
         }
         __syncthreads();
+        const bool packed = try_packed && S.rare == 0u;
+        if (try_packed && !packed) {                       // uniform, rare: N, IUPAC, lower case ... -> byte form after all
+            load_pieces(A, W0, xw, full, w);               // (the registers were not kept across the barrier)
+            compact_bytes<HPC>(S, xft, w, k16, qj);
+            __syncthreads();
+        }
         PHASE(4);
         const uint32_t tn = S.next[par ^ 1];
 #ifndef S2K_EMU
@@ -772,12 +966,16 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                     }
                 }
                 if (v0 == 0) invalid[0] |= lowmask64((uint32_t)dlt);   // the pseudo-owners inside the halo
-                const uint8_t *cb = S.code + XB + hk + v0 - d;     // cb[i]: last base of owner i's l-mer; 4-aligned
-                const uint32_t rare = hash_owners_words<W31, DENSE>(S, xft, cb, l, A.thr, hs + v0, mask);
-                if (rare & RARE4) {                                // a rare class among the bytes touched: redo via xy
+                if (packed) {
+                    hash_owners_packed<W31, DENSE>(S, xft, XB + hk + v0 - d, l, A.thr, hs + v0, mask);
+                } else {
+                    const uint8_t *cb = S.code + XB + hk + v0 - d; // cb[i]: last base of owner i's l-mer; 4-aligned
+                    const uint32_t rare = hash_owners_words<W31, DENSE>(S, xft, cb, l, A.thr, hs + v0, mask);
+                    if (rare & RARE4) {                            // a rare class among the bytes touched: redo via xy
 #pragma unroll
-                    for (int x = 0; x < MW; ++x) mask[x] = 0ull;
-                    hash_owners_bytes<W31>(S, cb, l, A.thr, hs + v0, mask);
+                        for (int x = 0; x < MW; ++x) mask[x] = 0ull;
+                        hash_owners_bytes<W31>(S, cb, l, A.thr, hs + v0, mask);
+                    }
                 }
 #pragma unroll
                 for (int x = 0; x < MW; ++x)                       // owners >= n_u hashed garbage
@@ -818,6 +1016,10 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
             }
         }
         __syncthreads();                                   // hit masks and prefixes of all threads are in place
+        if (try_packed) {                                  // the packed array has been read: clean for the next tile's ORs
+            for (int i = tid; i < PKW / 4; i += NT) reinterpret_cast<uint4 *>(S.pk)[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (tid == 0) S.rare = 0u;
+        }
         if (tid == 0) {
             S.rec0 = r0; S.rec_lim = lim;                  // read after the barrier inside the emission loop
             A.tile_info[t] = make_uint4(tile_min, wk - hk_real, (uint32_t)r0, (uint32_t)(r0 >> 32));
