@@ -106,13 +106,16 @@ impl GpuContext {
         if st == 0 { Ok(()) } else { Err(io_err(st, unsafe { s2k_last_error(self.0) })) }
     }
     /// Share of host slabs packed to 2 bits/base before crossing PCIe, and the threads doing it.
-    pub fn set_transport(&self, host_threads: i32, pack_ratio: f64) -> std::io::Result<()> {
+    pub fn set_transport(&mut self, host_threads: i32, pack_ratio: f64) -> std::io::Result<()> {
         self.check(unsafe { s2k_ctx_set_transport(self.0, host_threads, pack_ratio) })
     }
-    pub fn set_flags(&self, flags: u32) -> std::io::Result<()> { self.check(unsafe { s2k_ctx_set_flags(self.0, flags) }) }
+    pub fn set_flags(&mut self, flags: u32) -> std::io::Result<()> { self.check(unsafe { s2k_ctx_set_flags(self.0, flags) }) }
 
     /// `encode_rle_simd` over a batch (`src/hpc.rs:44-147`): (kept bytes, run starts, per-sequence offsets).
-    pub fn encode_rle(&self, bases: &[u8], seq_off: &[u64]) -> std::io::Result<(Vec<u8>, Vec<u32>, Vec<u64>)> {
+    /// Takes `&mut self`: a run reallocates the context's result buffers, so no `KminmersBatchIterator` (which points into
+    /// them) may be alive -- the exclusive borrow lets the compiler enforce that.
+    pub fn encode_rle(&mut self, bases: &[u8], seq_off: &[u64]) -> std::io::Result<(Vec<u8>, Vec<u32>, Vec<u64>)> {
+        assert!(!seq_off.is_empty() && seq_off[0] == 0 && *seq_off.last().unwrap() as usize <= bases.len());
         let mut r: S2kRleResult = unsafe { std::mem::zeroed() };
         self.check(unsafe { s2k_encode_rle(self.0, bases.as_ptr(), seq_off.as_ptr(), (seq_off.len() - 1) as u64, &mut r) })?;
         let n = r.n_hpc as usize;
@@ -133,17 +136,18 @@ pub fn bounds(density: f64) -> (u32, u32, u32) {
 
 /// Batched variant of `KminmersIterator`: one call for many reads; yields `(read index, KminmerHash)` in the order
 /// `for read in reads { for kminmer in KminmersIterator::new(read, l, k, density, mode) { .. } }` would.
-/// The result buffers belong to the context and stay valid until its next run, hence the borrow.
-pub struct KminmersBatchIterator<'c> { _ctx: &'c GpuContext, res: S2kResult, read: usize, i: u64 }
+/// The result buffers belong to the context and are reallocated by its next run: the iterator holds the context's
+/// EXCLUSIVE borrow, so safe code cannot start another run (or `encode_rle`) while it is alive.
+pub struct KminmersBatchIterator<'c> { _ctx: &'c mut GpuContext, res: S2kResult, read: usize, i: u64 }
 
 impl<'c> KminmersBatchIterator<'c> {
     /// `bases`: concatenated reads (ASCII); `seq_off`: n+1 offsets starting at 0.  Mirrors `KminmersIterator::new`
     /// (`src/lib.rs:89`); where the reference panics (`l > 31` in the SIMD modes, `l >= 256`) this returns `Err`.
-    pub fn new(ctx: &'c GpuContext, bases: &[u8], seq_off: &[u64], l: usize, k: usize, density: f64, mode: HashMode)
+    pub fn new(ctx: &'c mut GpuContext, bases: &[u8], seq_off: &[u64], l: usize, k: usize, density: f64, mode: HashMode)
         -> std::io::Result<Self> {
         Self::with_variant(ctx, bases, seq_off, l, k, density, mode, HashVariant::Nt1_32)
     }
-    pub fn with_variant(ctx: &'c GpuContext, bases: &[u8], seq_off: &[u64], l: usize, k: usize, density: f64,
+    pub fn with_variant(ctx: &'c mut GpuContext, bases: &[u8], seq_off: &[u64], l: usize, k: usize, density: f64,
                         mode: HashMode, variant: HashVariant) -> std::io::Result<Self> {
         assert!(!seq_off.is_empty() && *seq_off.last().unwrap() as usize <= bases.len());
         let p = S2kParams { l: l as u32, k: k as u32, density, mode: mode as i32, variant: variant as i32 };
@@ -152,15 +156,16 @@ impl<'c> KminmersBatchIterator<'c> {
         Ok(Self { _ctx: ctx, res, read: 0, i: 0 })
     }
     /// Reads already packed four bases per byte (A=0 C=1 T=2 G=3, `s2k_pack2`): a quarter of the PCIe bytes.
-    pub fn from_packed2(ctx: &'c GpuContext, packed: &[u8], seq_off: &[u64], l: usize, k: usize, density: f64,
+    pub fn from_packed2(ctx: &'c mut GpuContext, packed: &[u8], seq_off: &[u64], l: usize, k: usize, density: f64,
                         mode: HashMode) -> std::io::Result<Self> {
+        assert!(!seq_off.is_empty() && seq_off[0] == 0 && (*seq_off.last().unwrap() as usize + 3) / 4 <= packed.len());
         let p = S2kParams { l: l as u32, k: k as u32, density, mode: mode as i32, variant: 0 };
         let mut res: S2kResult = unsafe { std::mem::zeroed() };
         ctx.check(unsafe { s2k_run_packed2(ctx.0, packed.as_ptr(), seq_off.as_ptr(), (seq_off.len() - 1) as u64, &p, &mut res) })?;
         Ok(Self { _ctx: ctx, res, read: 0, i: 0 })
     }
     /// The file mode of `src/main.rs:50-81`: `parallel_fastx(&filename, nb_threads, task)` and the iterator per record.
-    pub fn from_fastx(ctx: &'c GpuContext, path: &str, nb_threads: usize, l: usize, k: usize, density: f64,
+    pub fn from_fastx(ctx: &'c mut GpuContext, path: &str, nb_threads: usize, l: usize, k: usize, density: f64,
                       mode: HashMode) -> std::io::Result<Self> {
         let c = CString::new(path).map_err(|e| std::io::Error::new(std::io::ErrorKind::InvalidInput, e))?;
         let p = S2kParams { l: l as u32, k: k as u32, density, mode: mode as i32, variant: 0 };

@@ -56,7 +56,8 @@ typedef enum s2k_hash_variant {
 #define S2K_ERR_L_TOO_BIG    -2
 #define S2K_ERR_CUDA         -3
 #define S2K_ERR_OOM          -4
-#define S2K_ERR_BAD_OFFSETS  -5   /* seq_off[0] != 0, decreasing offsets, or a sequence of >= 2^32 bases */
+#define S2K_ERR_BAD_OFFSETS  -5   /* seq_off[0] != 0, decreasing offsets, or a sequence of >= 2^32-1 bases (host entry points;
+                                     s2k_run_device trusts its device-resident offsets: see there) */
 #define S2K_ERR_INTERNAL     -6   /* device-side consistency check failed */
 #define S2K_ERR_NULL         -7
 #define S2K_ERR_IO           -8
@@ -108,8 +109,9 @@ typedef struct s2k_ctx s2k_ctx;
 
 /* Flags for s2k_ctx_set_flags. */
 #define S2K_WANT_MINIMIZERS 1u  /* s2k_run (host) also copies the minimizer stream back */
-#define S2K_GENERAL_KERNEL  4u  /* accepted and ignored: there is one minimizer kernel (an earlier raw-space variant that
-                                   this flag bypassed was measured slower and removed) */
+#define S2K_RLE_SCALAR_RULE 4u  /* s2k_encode_rle: the rule of the scalar `encode_rle` (src/hpc.rs:14): a repeated byte is
+                                   dropped only if it is one of "ACTGactgNn"; default = `encode_rle_simd` / `hpc`
+                                   (src/hpc.rs:33,86-95): every repeated byte is dropped */
 #define S2K_DEBUG_TINY_CAP  8u  /* tests only: start with room for 1000 minimizers so that the grow-and-rerun path runs */
 #define S2K_NO_MINIMIZER_STREAM 16u /* s2k_run_device: do not materialise the ordered minimizer stream (result.minimizers
                                    is NULL; items, km_off, min_off, min_cnt are unchanged).  The records stay where the
@@ -170,7 +172,9 @@ int s2k_last_transport(const s2k_ctx *ctx, uint64_t *h2d_bytes, uint64_t *packed
 
 /* Same, DEVICE buffers already resident in HBM (bases 16-byte aligned); results stay on the device.
  * `stream` is a cudaStream_t (NULL = the context's own stream).  Returns after the launch sequence has been
- * enqueued and the two scalar totals have been read back (one stream synchronisation). */
+ * enqueued and the scalar totals have been read back.  d_seq_off is TRUSTED (it lives on the device): it must start at
+ * 0, be non-decreasing, end at n_bases, and every sequence must be shorter than 2^32-1 bases (coordinates are u32);
+ * the host entry points check the same conditions and return S2K_ERR_BAD_OFFSETS. */
 int s2k_run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs,
                    uint64_t n_bases, const s2k_params *params, void *stream, s2k_result *out);
 
@@ -208,9 +212,6 @@ const char *s2k_strerror(int status);
 int s2k_abi_version(void);
 /* Kernels launched by the context since creation (for benchmark bookkeeping). */
 uint64_t s2k_launch_count(const s2k_ctx *ctx);
-/* Which minimizer kernel the last run used: always 0 = k_minimizers (values 1 and 2 belonged to a raw-space variant
- * that was measured slower and removed; the entry point stays for ABI stability). */
-int s2k_last_kernel_kind(const s2k_ctx *ctx);
 /* Name and average duration (ms) of the context's dominant kernel over the last s2k_run_device call,
  * measured with CUDA events on the launching stream when timing is enabled. */
 int s2k_ctx_set_timing(s2k_ctx *ctx, int enabled);

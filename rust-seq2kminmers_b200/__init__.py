@@ -81,7 +81,7 @@ ABI_SYMBOLS = (
     "s2k_ctx_create", "s2k_ctx_destroy", "s2k_ctx_set_flags", "s2k_run", "s2k_run_device", "s2k_encode_rle",
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
-    "s2k_ctx_set_slab_bytes", "s2k_last_kernel_kind", "s2k_run_fastx", "s2k_last_fastx", "s2k_ctx_set_transport",
+    "s2k_ctx_set_slab_bytes", "s2k_run_fastx", "s2k_last_fastx", "s2k_ctx_set_transport",
     "s2k_last_transport", "s2k_run_packed2", "s2k_pack2",
 )
 
@@ -139,8 +139,6 @@ class Library:
         L.s2k_run_fastx.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(_Params), C.POINTER(_Result)]
         L.s2k_last_fastx.restype = C.c_int
         L.s2k_last_fastx.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
-        L.s2k_last_kernel_kind.restype = C.c_int
-        L.s2k_last_kernel_kind.argtypes = [vp]
         L.s2k_synth_device.restype = C.c_int
         L.s2k_synth_device.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
         L.s2k_last_kernel_ms.restype = C.c_int
@@ -275,7 +273,7 @@ class Context:
     # -- host buffers in, host (pinned) results out ------------------------------------------------------
     def run(self, bases, seq_off, l: int, k: int, density: float, mode: HashMode,
             variant: HashVariant = HashVariant.NT1_32, want_minimizers: bool = False, copy: bool = True,
-            no_tail_rule: bool = False, general_kernel: bool = False, debug_tiny_cap: bool = False,
+            no_tail_rule: bool = False, debug_tiny_cap: bool = False,
             packed2: bool = False) -> KminmersBatch:
         """packed2=True: `bases` is 2-bit packed input (see pack2 / s2k_run_packed2), seq_off still counts bases."""
         b = _as_u8(bases)
@@ -286,7 +284,7 @@ class Context:
         if (int(so[-1]) + 3) // 4 > b.shape[0] if packed2 else int(so[-1]) > b.shape[0]:
             raise ValueError("seq_off[-1] exceeds len(bases)")
         self._check(self.lib.c.s2k_ctx_set_flags(self.h, (1 if want_minimizers else 0) | (2 if no_tail_rule else 0) |
-                                                 (4 if general_kernel else 0) | (8 if debug_tiny_cap else 0)))
+                                                 (8 if debug_tiny_cap else 0)))
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
         try:
@@ -313,14 +311,13 @@ class Context:
     # -- device buffers in, device results out ------------------------------------------------------------
     def run_device(self, d_bases_ptr: int, d_seq_off_ptr: int, n_seqs: int, n_bases: int, l: int, k: int,
                    density: float, mode: HashMode, variant: HashVariant = HashVariant.NT1_32, stream: int = 0,
-                   no_tail_rule: bool = False, general_kernel: bool = False, no_minimizer_stream: bool = False) -> _Result:
+                   no_tail_rule: bool = False, no_minimizer_stream: bool = False) -> _Result:
         """Raw device-pointer form (pointers as ints).  Returns the ctypes result struct (device pointers).
         no_minimizer_stream (S2K_NO_MINIMIZER_STREAM): result.minimizers is NULL, the window stage reads the minimizer
         records in place (one pass over them less); everything else in the result is unchanged."""
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
-        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (2 if no_tail_rule else 0) | (4 if general_kernel else 0) |
-                                                 (16 if no_minimizer_stream else 0)))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, (2 if no_tail_rule else 0) | (16 if no_minimizer_stream else 0)))
         try:
             self._check(self.lib.c.s2k_run_device(self.h, C.c_void_p(d_bases_ptr), C.c_void_p(d_seq_off_ptr), int(n_seqs),
                                                   int(n_bases), C.byref(p), C.c_void_p(stream), C.byref(r)))
@@ -351,12 +348,18 @@ class Context:
         self._check(self.lib.c.s2k_synth_device(self.h, int(seed), int(first), int(count), C.c_void_p(d_out_ptr),
                                                 C.c_void_p(stream)))
 
-    def encode_rle(self, bases, seq_off):
+    def encode_rle(self, bases, seq_off, scalar_rule: bool = False):
+        """Batched encode_rle_simd (src/hpc.rs:44); scalar_rule=True (S2K_RLE_SCALAR_RULE): the rule of the scalar
+        encode_rle (src/hpc.rs:14), where only repeated bytes out of "ACTGactgNn" are dropped."""
         b = _as_u8(bases)
         so = np.ascontiguousarray(seq_off, dtype=np.uint64)
         n = so.shape[0] - 1
         r = _RleResult()
-        self._check(self.lib.c.s2k_encode_rle(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(r)))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 4 if scalar_rule else 0))
+        try:
+            self._check(self.lib.c.s2k_encode_rle(self.h, b.ctypes.data, so.ctypes.data, n, C.byref(r)))
+        finally:
+            self.lib.c.s2k_ctx_set_flags(self.h, 0)
         return (_view(r.hpc, r.n_hpc, np.uint8).copy(), _view(r.pos, r.n_hpc, np.uint32).copy(),
                 _view(r.hpc_off, n + 1, np.uint64).copy())
 
@@ -381,11 +384,6 @@ class Context:
         a, b, n = C.c_double(), C.c_double(), C.c_uint32()
         self._check(self.lib.c.s2k_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
-
-    @property
-    def last_kernel_kind(self) -> int:
-        """0 general kernel, 1 raw-space fast kernel, 2 fast kernel declined and the general one reran."""
-        return int(self.lib.c.s2k_last_kernel_kind(self.h))
 
     @property
     def launch_count(self) -> int:
@@ -485,9 +483,12 @@ def encode_rle_simd(seq, ctx: Optional[Context] = None):
 
 
 def encode_rle(seq, ctx: Optional[Context] = None):
-    """src/hpc.rs:7: same keep rule on ACGTN input; positions widened to u64 like Vec<usize>."""
-    h, p = encode_rle_simd(seq, ctx)
-    return h, p.astype(np.uint64)
+    """src/hpc.rs:7-25: runs collapse only for bytes out of "ACTGactgNn" (src/hpc.rs:14); positions widened to u64 like
+    Vec<usize>."""
+    s = _as_u8(seq)
+    ctx = ctx or _default_ctx()
+    h, p, _ = ctx.encode_rle(s, np.array([0, s.shape[0]], dtype=np.uint64), scalar_rule=True)
+    return h.tobytes(), p.astype(np.uint64)
 
 
 def hpc(seq, ctx: Optional[Context] = None) -> bytes:

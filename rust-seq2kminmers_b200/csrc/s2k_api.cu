@@ -93,7 +93,6 @@ struct s2k_ctx {
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
     bool attr_set = false;
-    int kernel_kind = 0;            // last run: always 0 (one minimizer kernel); kept for ABI stability
     // pipelined host path (s2k_run on large batches)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_free[3] = {nullptr, nullptr, nullptr}, ev_out = nullptr, ev_done = nullptr;
@@ -395,7 +394,6 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     uint32_t n_tiles = 0, tile_eff = 0;
     uint64_t tmp_records = 0;                          // records d_tmp holds in the layout of the last launch
     bool regions = true;                               // per-CTA append regions first; one global allocator on the rerun
-    ctx->kernel_kind = 0;
     for (int attempt = 0;; ++attempt) {
         if (attempt == 4) return fail(ctx, S2K_ERR_INTERNAL, "minimizer kernel did not converge");
         tile_eff = P.tile;
@@ -686,7 +684,6 @@ extern "C" int s2k_debug_phase_clocks(unsigned long long *out16)
 }
 #endif
 
-int s2k_last_kernel_kind(const s2k_ctx *ctx) { return ctx ? ctx->kernel_kind : -1; }
 
 int s2k_host_alloc(size_t bytes, void **out)
 {
@@ -1397,7 +1394,12 @@ int s2k_encode_rle(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, 
     A.status = ptr<uint64_t>(ctx->d_status); A.ticket = reinterpret_cast<uint32_t *>(small + 4);
     A.err = reinterpret_cast<uint32_t *>(small + 5);
     A.hpc = ptr<uint8_t>(ctx->d_rle_hpc); A.pos = ptr<uint32_t>(ctx->d_rle_pos); A.hpc_off = ptr<uint64_t>(ctx->d_hpc_off);
+    A.scalar_rule = (ctx->flags & S2K_RLE_SCALAR_RULE) ? 1u : 0u;
+    timing_prepare(ctx);
+    Timing &T = ctx->tm;
+    if (T.enabled) cudaEventRecord(T.ev[0][0], st);
     S2K_LAUNCH(k_rle, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 8), NT, 0, st, false, A);
+    if (T.enabled) { cudaEventRecord(T.ev[0][1], st); T.n = 1; }
     CU(cudaGetLastError());
     ctx->launches += 2;
     CU(cudaMemcpyAsync(ctx->h_min_off.p, ctx->d_hpc_off.p, (n_seqs + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -1410,6 +1412,10 @@ int s2k_encode_rle(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, 
     CU(cudaMemcpyAsync(ctx->h_rle_hpc.p, ctx->d_rle_hpc.p, n_hpc, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ctx->h_rle_pos.p, ctx->d_rle_pos.p, n_hpc * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (ctx->tm.enabled && ctx->tm.n == 1) {               // s2k_last_kernel_ms: minimizer_ms = k_rle here
+        float f = 0; cudaEventElapsedTime(&f, ctx->tm.ev[0][0], ctx->tm.ev[0][1]);
+        ctx->tm.min_ms = f; ctx->tm.win_ms = 0; ctx->tm.min_launches = 1;
+    }
     out->n_hpc = n_hpc;
     out->hpc = ptr<uint8_t>(ctx->h_rle_hpc);
     out->pos = ptr<uint32_t>(ctx->h_rle_pos);

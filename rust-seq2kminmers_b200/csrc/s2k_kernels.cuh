@@ -1520,10 +1520,26 @@ struct K4Args {
     const uint32_t *tile_lb;
     uint64_t n_seqs, n_bases;
     uint32_t n_tiles;
+    uint32_t scalar_rule;          // S2K_RLE_SCALAR_RULE: only runs of "ACTGactgNn" collapse (src/hpc.rs:14)
     uint64_t *status; uint32_t *ticket; uint32_t *err;
     uint8_t  *hpc; uint32_t *pos; uint64_t *hpc_off;
 };
 constexpr int RLE_TILE = NT * 32;
+// bit b of the result: byte b of the 32 bytes in w[0..7] is one of "ACTGactgNn" (upper-cased: A C G T N)
+__device__ __forceinline__ uint32_t rle_collapsible(const uint32_t (&w)[8])
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = ((w[i] >> (8 * j)) & 0xffu) & 0xdfu;            // fold the case bit
+            const bool in = c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N';
+            m |= (in ? 1u : 0u) << (4 * i + j);
+        }
+    }
+    return m;
+}
 __global__ void __launch_bounds__(NT) k_rle(const __grid_constant__ K4Args A)
 {
     S2K_SHARED uint32_t startw[NT];
@@ -1542,23 +1558,39 @@ __global__ void __launch_bounds__(NT) k_rle(const __grid_constant__ K4Args A)
         const bool last_tile = T1 == A.n_bases;
         const uint32_t lb = A.tile_lb[t], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
         startw[tid] = 0;
+        // this thread's 32 bases: two 16-byte loads (the batch is 16-byte aligned, RLE_TILE a multiple of 32)
+        const uint64_t g0 = T0 + 32ull * tid;
+        uint32_t w[8];
+        if (g0 + 32 <= A.n_bases) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(A.bases + g0)), y = __ldg(reinterpret_cast<const uint4 *>(A.bases + g0) + 1);
+            w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t x = 0;
+                for (int j = 0; j < 4; ++j) { const uint64_t g = g0 + 4 * i + j; if (g < A.n_bases) x |= (uint32_t)A.bases[g] << (8 * j); }
+                w[i] = x;
+            }
+        }
         __syncthreads();
         for (uint32_t i = lb + tid; i < ub; i += NT) {
             const uint64_t so = A.seq_off[i];
             if (so < T1) { const uint32_t x = (uint32_t)(so - T0); atomicOr(&startw[x >> 5], 1u << (x & 31)); }
         }
         __syncthreads();
-        const uint64_t g0 = T0 + 32ull * tid;
+        // keep bit = byte differs from the byte before it (word-wise, as in k_minimizers), or starts a sequence
+        uint32_t prevw = __shfl_up_sync(0xffffffffu, w[7], 1);
+        if (lane == 0) prevw = ((g0 > 0 && g0 <= A.n_bases) ? (uint32_t)A.bases[g0 - 1] : 0u) << 24;
         uint32_t keep = 0;
-        uint8_t by[32];
-        uint8_t prev = (g0 > 0 && g0 <= A.n_bases) ? A.bases[g0 - 1] : 0;
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            const uint64_t g = g0 + b;
-            by[b] = g < T1 ? A.bases[g] : 0;
-            if (g < T1 && (by[b] != prev || ((startw[tid] >> b) & 1u))) keep |= 1u << b;
-            prev = by[b];
+        for (int i = 7; i >= 0; --i) {
+            const uint32_t x = w[i] ^ __byte_perm(i ? w[i - 1] : prevw, w[i], 0x6543u);
+            const uint32_t nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+            keep = __funnelshift_l(nz * 0x00204081u, keep, 4);
         }
+        if (A.scalar_rule) keep |= ~rle_collapsible(w);      // a repeated byte outside "ACTGactgNn" is kept
+        keep |= startw[tid];
+        if (g0 + 32 > T1) keep &= g0 < T1 ? lowmask((uint32_t)(T1 - g0)) : 0u;
         uint32_t incl = warp_incl_scan(__popc(keep), lane);
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
@@ -1606,7 +1638,7 @@ __global__ void __launch_bounds__(NT) k_rle(const __grid_constant__ K4Args A)
                 if ((keep >> b) & 1u) {
                     const uint64_t g = g0 + b;
                     while (g >= nx) { ++rid; so = A.seq_off[rid]; nx = A.seq_off[rid + 1]; }
-                    A.hpc[o] = by[b];
+                    A.hpc[o] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
                     A.pos[o] = (uint32_t)(g - so);
                     ++o;
                 }

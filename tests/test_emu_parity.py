@@ -24,6 +24,18 @@ def test_emulated_rle_matches_oracle(S, O, emu_ctx, batches, fixture_seq):
         eh, ep = O.encode_rle_simd(s)
         a, b = int(off[i]), int(off[i + 1])
         assert h[a:b].tobytes() == eh and np.array_equal(p[a:b], ep), i
+    # the scalar encode_rle (src/hpc.rs:14) collapses runs of "ACTGactgNn" only: junk bytes repeat in its output
+    seqs = [batches.seq(4000, alphabet=b"ACGTNacgtnXX--RY", runp=0.6), batches.seq(0), np.full(300, ord("X"), np.uint8),
+            batches.seq(700, alphabet=b"AX", runp=0.5), fixture_seq[:5000]]
+    bases, so = batches.pack(seqs)
+    h, p, off = emu_ctx.encode_rle(bases, so, scalar_rule=True)
+    for i, s in enumerate(seqs):
+        if len(s) == 0:
+            assert off[i] == off[i + 1]
+            continue
+        eh, ep = O.encode_rle(s)
+        a, b = int(off[i]), int(off[i + 1])
+        assert h[a:b].tobytes() == eh and np.array_equal(p[a:b].astype(np.uint64), np.asarray(ep, dtype=np.uint64)), i
 
 
 def test_split_invariance_emulated(S, O, emu_ctx, batches):
