@@ -87,7 +87,7 @@ struct s2k_ctx {
     int sm_count = 148;
     double rate_hint = 0.0;         // observed minimizers per base (grow-only)
     // device buffers
-    Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_hpc_off, d_km_off, d_min_cnt;
+    Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_min_loc, d_tile_pre, d_hpc_off, d_km_off, d_min_cnt;
     Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr, d_tmp, d_tile_info, d_tile_base, d_tile_src;
     // pinned host result buffers
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
@@ -391,28 +391,45 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         if (ctx->flags & S2K_DEBUG_TINY_CAP) cap = std::min<uint64_t>(cap, 1000);
     }
 
-    uint32_t n_tiles = 0, tile_eff = 0;
-    uint64_t tmp_records = 0;                          // records d_tmp holds in the layout of the last launch
+    // The whole launch sequence is enqueued without a host round trip: every buffer is sized from `cap`, the kernels
+    // after k_minimizers read the minimizer total from the device and do nothing once the record store has overflowed
+    // (ERR_CAP); ONE synchronisation at the end brings back the totals and the error word.  An overflow (the batch is
+    // denser than the expected selection rate, or one CTA's append region ran out) reruns the sequence once with the
+    // exact size and a single global allocator.
+    const uint64_t tile_eff = P.tile;
+    const uint64_t n_tiles64 = (n_bases + tile_eff - 1) / tile_eff;
+    if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+    const int max_grid = ctx->sm_count * S2K_MINB;
+    const size_t hscr_words = (size_t)max_grid * WIN, smem = sizeof(Smem);
+    void (*kfn)(const K1Args) = minimizer_kernel(P.hpc, P.w31, P.dense);
+    const uint32_t n_chunks = (n_tiles + ST - 1) / ST;
+    const uint64_t rtiles = (n_seqs + RT * RPT - 1) / (RT * RPT);
+    if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_min_loc, (n_seqs + 1) * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tile_pre, ((uint64_t)n_tiles + 1) * sizeof(ulonglong2), false))) return rc;
+    if (in_place && (rc = ensure(ctx, ctx->d_tile_src, (uint64_t)n_tiles * sizeof(ulonglong2), false))) return rc;
+    // d_tile_base: [tile_loc u64 x n_tiles][chunk_tot u64 x n_chunks][chunk_base u64x2 x (n_chunks+1)]
+    if ((rc = ensure(ctx, ctx->d_tile_base, ((uint64_t)n_tiles + n_chunks + 2) * 8 + ((uint64_t)n_chunks + 1) * 16 + 16, false))) return rc;
+
     bool regions = true;                               // per-CTA append regions first; one global allocator on the rerun
     for (int attempt = 0;; ++attempt) {
         if (attempt == 4) return fail(ctx, S2K_ERR_INTERNAL, "minimizer kernel did not converge");
-        tile_eff = P.tile;
-        const uint64_t n_tiles64 = (n_bases + tile_eff - 1) / tile_eff;
-        if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
-        n_tiles = (uint32_t)n_tiles64;
-        const int max_grid = ctx->sm_count * S2K_MINB;
-        const size_t hscr_words = (size_t)max_grid * WIN, smem = sizeof(Smem);
-        void (*kfn)(const K1Args) = minimizer_kernel(P.hpc, P.w31, P.dense);
-        if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
-        if ((rc = ensure(ctx, ctx->d_tile_info, (uint64_t)n_tiles * 16, false))) return rc;
-        if ((rc = ensure(ctx, ctx->d_hscr, hscr_words * 4, false))) return rc;
         // Per-CTA append regions get 1/8 + 1024 records of slack on top of an even share: tiles are handed out
         // dynamically, so the CTAs' totals differ by a few tiles' worth.
         const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
         const uint64_t slack = (ctx->flags & S2K_DEBUG_TINY_CAP) ? 1 : cap / (8ull * (uint64_t)grid) + 1024;
         const uint64_t region_cap = regions ? cap / (uint64_t)grid + slack : 0;
         const uint64_t tmp_cap = regions ? region_cap * (uint64_t)grid : cap;
+        const uint64_t item_cap = std::max<uint64_t>(cap, 1);
         if ((rc = ensure(ctx, ctx->d_tmp, tmp_cap * sizeof(uint4), false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_mins, (in_place ? 1 : item_cap) * sizeof(uint4), false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_hash, item_cap * 8, false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_start, item_cap * 4, false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_end, item_cap * 4, false))) return rc;
+        if ((rc = ensure(ctx, ctx->d_rev, item_cap, false))) return rc;
 
         K1Args A;
         A.bases = d_bases; A.seq_off = d_seq_off;
@@ -421,20 +438,20 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.cursor = reinterpret_cast<unsigned long long *>(small + 0);
         A.tile_info = ptr<uint4>(ctx->d_tile_info);
         A.min_out = ptr<uint4>(ctx->d_tmp); A.min_cap = tmp_cap;
-        tmp_records = tmp_cap;
         A.region_cap = region_cap;
-        A.min_off = ptr<uint64_t>(ctx->d_min_off);
+        A.min_off = ptr<uint64_t>(ctx->d_min_loc);
         A.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
         A.hscr = ptr<uint32_t>(ctx->d_hscr);
         A.err = reinterpret_cast<uint32_t *>(small + 5);
         A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
-        A.tile = tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
+        A.tile = (uint32_t)tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
         std::memcpy(A.cls_lut, P.lut, 256);
         std::memcpy(A.xy, P.xy, sizeof(P.xy));
         std::memcpy(A.xf, P.xf, sizeof(P.xf));
         std::memcpy(A.x2, P.x2, sizeof(P.x2));
         CU(cudaMemsetAsync(small, 0, 64, st));
-        S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, n_bases, tile_eff, n_tiles,
+        CU(cudaMemsetAsync(ctx->d_status.p, 0, rtiles * 8, st));
+        S2K_LAUNCH(k_tile_bounds, (n_tiles + 1 + 255) / 256, 256, 0, st, false, d_seq_off, n_seqs, n_bases, (uint32_t)tile_eff, n_tiles,
                    ptr<uint32_t>(ctx->d_tile_lb));
         Timing &T = ctx->tm;
         const bool rec = T.enabled && T.n < 64;
@@ -443,72 +460,51 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         if (rec) { cudaEventRecord(T.ev[T.n][1], st); ++T.n; }
         CU(cudaGetLastError());
         ctx->launches += 2;
-        CU(cudaMemcpyAsync(hsmall, small, 8, cudaMemcpyDeviceToHost, st));          // record cursor == total minimizers
-        CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        n_min = hsmall[0];
-        if ((uint32_t)hsmall[2] & ERR_ALIGN) return fail(ctx, S2K_ERR_INTERNAL, "shared-memory tables are not 256-byte aligned");
-        if (regions ? !((uint32_t)hsmall[2] & ERR_CAP) : n_min <= cap) break;
-        cap = std::max(cap, n_min);                    // exact size known now: rerun once, with one global allocator
-        regions = false;
-    }
-    if ((rc = ensure(ctx, ctx->d_mins, (in_place ? 1 : std::max<uint64_t>(n_min, 1)) * sizeof(uint4), false))) return rc;
-    if (in_place && (rc = ensure(ctx, ctx->d_tile_src, (uint64_t)n_tiles * sizeof(ulonglong2), false))) return rc;
-    {
-        const uint32_t n_chunks = (n_tiles + ST - 1) / ST;
-        // d_tile_base: [tile_loc u64 x n_tiles][chunk_tot u64 x n_chunks][chunk_base u64x2 x (n_chunks+1)]
-        if ((rc = ensure(ctx, ctx->d_tile_base, ((uint64_t)n_tiles + n_chunks + 2) * 8 + ((uint64_t)n_chunks + 1) * 16 + 16, false))) return rc;
+
+        // ---- tile order: exclusive prefix of the per-tile counts, where each tile's records belong
         unsigned long long *tile_loc = ptr<unsigned long long>(ctx->d_tile_base);
         unsigned long long *chunk_tot = tile_loc + n_tiles;
         ulonglong2 *chunk_base = reinterpret_cast<ulonglong2 *>(
             (reinterpret_cast<uintptr_t>(chunk_tot + n_chunks) + 15) & ~uintptr_t(15));
         S2K_LAUNCH(k_tile_scan_a, n_chunks, ST, 0, st, false, ptr<uint4>(ctx->d_tile_info), n_tiles, tile_loc, chunk_tot);
-        S2K_LAUNCH(k_tile_scan_b, 1, ST, 0, st, false, chunk_tot, n_chunks, chunk_base);
+        S2K_LAUNCH(k_tile_scan_b, 1, ST, 0, st, false, chunk_tot, n_chunks, chunk_base, (unsigned long long)cap, A.err);
         KFArgs F;
         F.tile_info = ptr<uint4>(ctx->d_tile_info); F.tile_loc = tile_loc; F.chunk_base = chunk_base;
-        F.tile_lb = ptr<uint32_t>(ctx->d_tile_lb); F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
-        F.min_off = ptr<uint64_t>(ctx->d_min_off); F.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
-        F.n_seqs = n_seqs; F.n_bases = n_bases; F.min_cap = tmp_records; F.n_tiles = n_tiles; F.tile = tile_eff;
+        F.tmp = ptr<uint4>(ctx->d_tmp); F.mins = ptr<uint4>(ctx->d_mins);
+        F.min_cap = tmp_cap; F.n_tiles = n_tiles;
+        F.tile_pre = ptr<ulonglong2>(ctx->d_tile_pre);
         F.tile_src = in_place ? ptr<ulonglong2>(ctx->d_tile_src) : nullptr; F.copy = in_place ? 0 : 1;
-        const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 8);
+        F.err = A.err;
+        const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 8) / 8, (uint64_t)ctx->sm_count * 8);
         S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
         CU(cudaGetLastError());
         ctx->launches += 3;
-    }
-    ctx->rate_hint = std::max(ctx->rate_hint, (double)n_min / (double)n_bases);
 
-    // window stage
-    const uint64_t item_cap = std::max<uint64_t>(n_min, 1);
-    if ((rc = ensure(ctx, ctx->d_hash, item_cap * 8, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_start, item_cap * 4, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_end, item_cap * 4, false))) return rc;
-    if ((rc = ensure(ctx, ctx->d_rev, item_cap, false))) return rc;
-    {
+        // ---- per-sequence prefixes and counts, then the window stage
         K2Args B;
         B.mins = in_place ? ptr<uint4>(ctx->d_tmp) : ptr<uint4>(ctx->d_mins);
-        B.tile_src = in_place ? ptr<ulonglong2>(ctx->d_tile_src) : nullptr; B.n_tiles = n_tiles; B.tile = tile_eff;
-        B.min_off = ptr<uint64_t>(ctx->d_min_off);
-        B.hpc_off = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+        B.tile_src = in_place ? ptr<ulonglong2>(ctx->d_tile_src) : nullptr; B.n_tiles = n_tiles; B.tile = (uint32_t)tile_eff;
+        B.tile_magic = ~0ull / tile_eff + 1;
+        B.min_loc = ptr<uint64_t>(ctx->d_min_loc);
+        B.hpc_loc = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
+        B.tile_pre = ptr<ulonglong2>(ctx->d_tile_pre);
         B.seq_off = d_seq_off; B.bases = d_bases; B.n_seqs = n_seqs;
         B.l = P.l; B.k = P.k; B.quirk = P.quirk; B.hpc = P.hpc;
+        B.min_off = ptr<uint64_t>(ctx->d_min_off);
         B.km_off = ptr<uint64_t>(ctx->d_km_off);
         B.min_cnt = ptr<uint32_t>(ctx->d_min_cnt);
         B.status = ptr<uint64_t>(ctx->d_status);
         B.ticket = reinterpret_cast<uint32_t *>(small + 6);
-        B.err = reinterpret_cast<uint32_t *>(small + 5);
-        const uint64_t rtiles = (n_seqs + RT * RPT - 1) / (RT * RPT);
-        CU(cudaMemsetAsync(B.status, 0, rtiles * 8, st));
-        CU(cudaMemsetAsync(B.ticket, 0, 4, st));
-        Timing &T = ctx->tm;
+        B.err = A.err;
         if (T.enabled) cudaEventRecord(T.wv[0], st);
-        const int grid = (int)std::min<uint64_t>(rtiles, (uint64_t)ctx->sm_count * 8);
-        S2K_LAUNCH(k_read_counts, grid, RT, 0, st, false, B);
+        const int grid2 = (int)std::min<uint64_t>(rtiles, (uint64_t)ctx->sm_count * 8);
+        S2K_LAUNCH(k_read_counts, grid2, RT, 0, st, false, B);
         CU(cudaGetLastError());
         K3Args C;
-        C.mins = B.mins; C.min_off = B.min_off; C.km_off = B.km_off; C.n_min = n_min; C.k = P.k;
+        C.mins = B.mins; C.min_off = B.min_off; C.km_off = B.km_off; C.n_min_p = A.cursor; C.err = A.err; C.k = P.k;
         C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);
         C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
-        if (n_min > 0 && in_place) {
+        if (in_place) {
             K3TArgs D;
             D.W = C; D.tile_info = ptr<uint4>(ctx->d_tile_info); D.tile_src = B.tile_src; D.n_tiles = n_tiles;
             const int g3 = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 16);
@@ -518,10 +514,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
                 S2K_WINDOWS_CASE(7) S2K_WINDOWS_CASE(8) S2K_WINDOWS_CASE(9) S2K_WINDOWS_CASE(10) S2K_WINDOWS_CASE(11) S2K_WINDOWS_CASE(12)
 #undef S2K_WINDOWS_CASE
             }
-            CU(cudaGetLastError());
-            ctx->launches += 1;
-        } else if (n_min > 0) {
-            const int g3 = (int)std::min<uint64_t>((n_min + 255) / 256, (uint64_t)ctx->sm_count * 16);
+        } else {
+            const int g3 = (int)std::min<uint64_t>((item_cap + 255) / 256, (uint64_t)ctx->sm_count * 16);
             switch (P.k <= (uint32_t)KW_MAX ? (int)P.k : 0) {
 #define S2K_WINDOWS_CASE(K) case K: S2K_LAUNCH(k_windows_w<K>, g3, 256, 0, st, false, C); break;
                 S2K_WINDOWS_CASE(1) S2K_WINDOWS_CASE(2) S2K_WINDOWS_CASE(3) S2K_WINDOWS_CASE(4) S2K_WINDOWS_CASE(5) S2K_WINDOWS_CASE(6)
@@ -529,16 +523,24 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
 #undef S2K_WINDOWS_CASE
                 default: S2K_LAUNCH(k_windows, g3, 256, 0, st, false, C);
             }
-            CU(cudaGetLastError());
-            ctx->launches += 1;
         }
+        CU(cudaGetLastError());
         if (T.enabled) cudaEventRecord(T.wv[1], st);
-        ctx->launches += 1;
+        ctx->launches += 2;
+        CU(cudaMemcpyAsync(hsmall, small, 8, cudaMemcpyDeviceToHost, st));             // record cursor == total minimizers
+        CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));     // error word
         CU(cudaMemcpyAsync(hsmall + 4, B.km_off + n_seqs, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(hsmall + 2, small + 5, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if ((uint32_t)hsmall[2] & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "scan look-back timed out");
+        n_min = hsmall[0];
+        const uint32_t errw = (uint32_t)hsmall[2];
+        if (errw & ERR_ALIGN) return fail(ctx, S2K_ERR_INTERNAL, "shared-memory tables are not 256-byte aligned");
+        if (errw & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "scan look-back timed out");
+        if (!(errw & ERR_CAP) && n_min <= cap) break;
+        cap = std::max(cap, n_min);                    // exact size known now: rerun once, with one global allocator
+        regions = false;
+        T.n = 0;
     }
+    ctx->rate_hint = std::max(ctx->rate_hint, (double)n_min / (double)n_bases);
     if (ctx->tm.enabled) {
         Timing &T = ctx->tm;
         double ms = 0;
@@ -629,7 +631,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     Buf *all[] = {&ctx->d_bases, &ctx->d_seq_off, &ctx->d_tile_lb, &ctx->d_status, &ctx->d_small, &ctx->d_mins,
-                  &ctx->d_min_off, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
+                  &ctx->d_min_off, &ctx->d_min_loc, &ctx->d_tile_pre, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
                   &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->d_tile_src, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in[2], &ctx->d_in_off[0], &ctx->d_in_off[1], &ctx->d_in_off[2],

@@ -1146,8 +1146,10 @@ __global__ void __launch_bounds__(ST) k_tile_scan_a(const uint4 *__restrict__ ti
     if (t < n_tiles) tile_loc[t] = pre + incl - v;
     if (tid == 0) chunk_tot[blockIdx.x] = tot;
 }
+// `cap`: records the result buffers were sized for; more minimizers than that raise ERR_CAP here, before any kernel
+// writes through the ordered indices.
 __global__ void __launch_bounds__(ST) k_tile_scan_b(const unsigned long long *__restrict__ chunk_tot, uint32_t n_chunks,
-                                                    ulonglong2 *__restrict__ chunk_base)
+                                                    ulonglong2 *__restrict__ chunk_base, unsigned long long cap, uint32_t *err)
 {
     S2K_SHARED unsigned long long sa[ST], sb[ST];
     S2K_SHARED unsigned long long carry[2];
@@ -1172,41 +1174,47 @@ __global__ void __launch_bounds__(ST) k_tile_scan_b(const unsigned long long *__
         if (tid == ST - 1) { carry[0] += sa[tid]; carry[1] += sb[tid]; }
     }
     __syncthreads();
-    if (tid == 0) chunk_base[n_chunks] = make_ulonglong2(carry[0], carry[1]);
+    if (tid == 0) {
+        chunk_base[n_chunks] = make_ulonglong2(carry[0], carry[1]);
+        if (carry[0] > cap) atomicOr(err, ERR_CAP);
+    }
 }
 
 struct KFArgs {
     const uint4 *tile_info;
     const unsigned long long *tile_loc;
     const ulonglong2 *chunk_base;
-    const uint32_t *tile_lb;
     const uint4 *tmp;
     uint4 *mins;
-    uint64_t *min_off, *hpc_off;
-    uint64_t n_seqs, n_bases, min_cap;
-    uint32_t n_tiles, tile;
+    uint64_t min_cap;
+    uint32_t n_tiles;
+    ulonglong2 *tile_pre;        // n_tiles + 1: (minimizers, kept bases) before the tile; entry n_tiles = the totals
     ulonglong2 *tile_src;        // or null: per tile (ordered index of its first record, where its records sit in tmp)
     int32_t copy;                // 0: leave the records where they are (the window stage reads them through tile_src)
+    const uint32_t *err;         // ERR_CAP set: the record store overflowed, the host reruns -- touch nothing
 };
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs A)
 {
+    if (*A.err & ERR_CAP) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < A.n_tiles; t += nwarps) {
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t <= A.n_tiles; t += nwarps) {
+        if (t == A.n_tiles) {                              // the totals, for sequences that start at the very end
+            const ulonglong2 tot = A.chunk_base[(A.n_tiles + ST - 1) / ST];
+            if (lane == 0) A.tile_pre[t] = tot;
+            continue;
+        }
         const uint4 info = A.tile_info[t];
         const ulonglong2 cb = A.chunk_base[t / ST];
         const unsigned long long loc = A.tile_loc[t];
         const uint64_t bm = cb.x + (loc & 0xffffffffull), bk = cb.y + (loc >> 32);
         const uint64_t src = ((uint64_t)info.w << 32) | info.z;
-        if (A.tile_src && lane == 0) A.tile_src[t] = make_ulonglong2(bm, src);
+        if (lane == 0) {
+            A.tile_pre[t] = make_ulonglong2(bm, bk);
+            if (A.tile_src) A.tile_src[t] = make_ulonglong2(bm, src);
+        }
         if (A.copy && src + info.x <= A.min_cap)
             for (uint32_t j = lane; j < info.x; j += 32) A.mins[bm + j] = A.tmp[src + j];
-        const bool last_tile = (uint64_t)(t + 1) * A.tile >= A.n_bases;
-        const uint32_t lb = A.tile_lb[t], ub = last_tile ? (uint32_t)(A.n_seqs + 1) : A.tile_lb[t + 1];
-        for (uint32_t i = lb + lane; i < ub; i += 32) {
-            A.min_off[i] += bm;
-            if (A.hpc_off) A.hpc_off[i] += bk;
-        }
     }
 }
 
@@ -1215,11 +1223,14 @@ constexpr int RT = 256;            // threads per CTA
 constexpr int RPT = 4;             // sequences per thread
 struct K2Args {
     const uint4    *mins;
-    const uint64_t *min_off, *hpc_off, *seq_off;
+    const uint64_t *min_loc, *hpc_loc;   // n_seqs + 1, tile-LOCAL prefixes written by k_minimizers (hpc_loc may be null)
+    const uint64_t *seq_off;
     const uint8_t  *bases;
+    const ulonglong2 *tile_pre;          // n_tiles + 1: (minimizers, kept bases) before each tile (k_finalize)
     uint64_t  n_seqs;
     uint32_t  l, k;
     int32_t   quirk, hpc;
+    uint64_t *min_off;             // n_seqs + 1, out: global exclusive prefix of per-sequence minimizer counts
     uint64_t *km_off;              // n_seqs + 1
     uint32_t *min_cnt;             // n_seqs
     uint64_t *status;              // per tile, zeroed
@@ -1227,7 +1238,19 @@ struct K2Args {
     uint32_t *err;
     const ulonglong2 *tile_src;    // non-null: `mins` is the unordered record store of k_minimizers (tiles contiguous,
     uint32_t  n_tiles, tile;       // in completion order) and ordered index m is looked up through tile_src
+    uint64_t  tile_magic;          // floor(2^64 / tile) + 1: position / tile as one 64-bit multiply-high (+ a fix-up)
 };
+// x / tile without the 64-bit division sequence (five of them per thread made k_read_counts 3x slower).
+__device__ __forceinline__ uint32_t tile_of_pos(const K2Args &A, uint64_t x)
+{
+#ifdef S2K_EMU
+    uint64_t q = (uint64_t)(((unsigned __int128)x * A.tile_magic) >> 64);
+#else
+    uint64_t q = __umul64hi(x, A.tile_magic);
+#endif
+    if (q * A.tile > x) --q;                               // the estimate is exact or one too large
+    return (uint32_t)q;
+}
 
 // Tile holding ordered record m: the largest t with tile_src[t].x <= m.  `hint` is a tile near it (the caller knows a
 // base position close to the minimizer): a step or two, except across runs of tiles without minimizers (a homopolymer
@@ -1252,49 +1275,48 @@ __device__ __forceinline__ uint32_t tile_of_record(const ulonglong2 *tile_src, u
     return t;
 }
 
-// Minimizers of sequence r that reach the window stage.  In the AVX-512 profile of ntHash1 the iterator
+// Minimizers of a sequence that reach the window stage.  In the AVX-512 profile of ntHash1 the iterator
 // masks the last block with (1 << (S % 16)) - 1 (src/nthash_avx512_32.rs:134-138): when S > 16 and
 // S % 16 == 0 the last 16 l-mer positions are lost.  Their minimizers are a suffix of the sequence's list:
-// exactly those whose last base is one of the final 16 kept bases.
-__device__ __forceinline__ uint32_t window_feed_count(const K2Args &A, uint64_t r)
+// exactly those whose last base is one of the final 16 kept bases.  Called by the threads whose sequence is under the
+// rule (one in sixteen): the lanes of a warp walk their own sequences side by side, the ~21 bases of a walk sit in one
+// or two cache lines.  (Measured alternatives, config 3: the last 64 bases as unrolled independent loads 8.8 ms, one
+// warp per sequence with ballots 5.4 ms, this 2.x ms for the whole kernel.)
+__device__ __forceinline__ uint32_t tail_rule_count(const K2Args &A, uint64_t so, uint64_t se, uint64_t m0, uint64_t cnt)
 {
-    const uint64_t m0 = A.min_off[r], m1 = A.min_off[r + 1];
-    uint64_t cnt = m1 - m0;
-    if (A.quirk && cnt > 0) {
-        const uint64_t so = A.seq_off[r], se = A.seq_off[r + 1];
-        const uint64_t M = A.hpc ? (A.hpc_off[r + 1] - A.hpc_off[r]) : (se - so);
-        if (M >= (uint64_t)A.l + 16 && ((M - A.l + 1) & 15) == 0) {
-            uint64_t e16;                                   // local position of the 16th kept base from the end
-            if (!A.hpc) {
-                e16 = (se - so) - 16;
-            } else {
-                uint64_t g = se;
-                int found = 0;
-                while (found < 16) {                        // M >= 16 guarantees termination above `so`
-                    --g;
-                    if (g == so || A.bases[g] != A.bases[g - 1]) ++found;
-                }
-                e16 = g - so;
-            }
-            if (!A.tile_src) {
-                while (cnt > 0 && (uint64_t)A.mins[m0 + cnt - 1].z >= e16) --cnt;
-            } else {
-                uint32_t t = (uint32_t)((se - 1) / A.tile);
-                while (cnt > 0) {
-                    const uint64_t m = m0 + cnt - 1;
-                    t = tile_of_record(A.tile_src, A.n_tiles, m, t);
-                    const ulonglong2 ts = A.tile_src[t];
-                    if ((uint64_t)A.mins[ts.y + (m - ts.x)].z < e16) break;
-                    --cnt;
-                }
-            }
+    uint64_t e16;                                       // local position of the 16th kept base from the end
+    if (!A.hpc) {
+        e16 = (se - so) - 16;
+    } else {
+        uint64_t g = se;
+        int found = 0;
+        while (found < 16) {                            // M >= 16 guarantees termination above `so`
+            --g;
+            if (g == so || A.bases[g] != A.bases[g - 1]) ++found;
+        }
+        e16 = g - so;
+    }
+    if (!A.tile_src) {
+        while (cnt > 0 && (uint64_t)A.mins[m0 + cnt - 1].z >= e16) --cnt;
+    } else {
+        uint32_t t = tile_of_pos(A, se - 1);
+        while (cnt > 0) {
+            const uint64_t m = m0 + cnt - 1;
+            t = tile_of_record(A.tile_src, A.n_tiles, m, t);
+            const ulonglong2 ts = A.tile_src[t];
+            if ((uint64_t)A.mins[ts.y + (m - ts.x)].z < e16) break;
+            --cnt;
         }
     }
     return (uint32_t)cnt;
 }
 
+// Per sequence: the tile-local prefixes of k_minimizers made global (the tile of a sequence = the tile of its first
+// base), minimizers that feed the window stage, item counts, and their exclusive scan (decoupled look-back over tiles
+// of RT * RPT sequences).  One pass over the per-sequence arrays: 16-24 bytes read, 20 written per sequence.
 __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Args A)
 {
+    if (*A.err & ERR_CAP) return;                          // the record store overflowed: the host reruns
     S2K_SHARED uint32_t wsum[RT / 32];
     S2K_SHARED unsigned long long s_excl;
     S2K_SHARED uint32_t s_tile;
@@ -1307,15 +1329,37 @@ __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Ar
         const uint32_t t = s_tile;
         if (t >= n_tiles) break;
         const uint64_t r0 = (uint64_t)t * (RT * RPT) + (uint64_t)tid * RPT;
+        uint64_t gm[RPT + 1], gk[RPT + 1];                 // global prefixes of sequences r0 .. r0 + RPT
+#pragma unroll
+        for (int j = 0; j <= RPT; ++j) {
+            gm[j] = 0; gk[j] = 0;
+            const uint64_t r = r0 + j;
+            if (r <= A.n_seqs) {
+                const uint64_t so = A.seq_off[r];
+                uint32_t ts = tile_of_pos(A, so);
+                if (ts >= A.n_tiles) ts = A.n_tiles - 1;
+                const ulonglong2 pre = A.tile_pre[ts];
+                gm[j] = A.min_loc[r] + pre.x;
+                gk[j] = A.hpc_loc ? A.hpc_loc[r] + pre.y : so;
+            }
+        }
         uint32_t items[RPT], sum = 0;
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             items[j] = 0;
             const uint64_t r = r0 + j;
+            uint32_t c = r < A.n_seqs ? (uint32_t)(gm[j + 1] - gm[j]) : 0u;
+            if (A.quirk && r < A.n_seqs && c > 0) {
+                const uint64_t M = gk[j + 1] - gk[j];
+                if (M >= (uint64_t)A.l + 16 && ((M - A.l + 1) & 15) == 0)
+                    c = tail_rule_count(A, A.seq_off[r], A.seq_off[r + 1], gm[j], c);
+            }
             if (r < A.n_seqs) {
-                const uint32_t c = window_feed_count(A, r);
                 A.min_cnt[r] = c;
+                A.min_off[r] = gm[j];
                 items[j] = c >= A.k ? c - A.k + 1 : 0;
+            } else if (r == A.n_seqs) {
+                A.min_off[r] = gm[j];
             }
             sum += items[j];
         }
@@ -1370,7 +1414,8 @@ __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Ar
 struct K3Args {
     const uint4    *mins;
     const uint64_t *min_off, *km_off;
-    uint64_t  n_min;
+    const unsigned long long *n_min_p;   // total minimizers, on the device (the record cursor of k_minimizers)
+    const uint32_t *err;                  // ERR_CAP set: the record store overflowed, the host reruns -- touch nothing
     uint32_t  k;
     uint64_t *hash;
     uint32_t *start, *end;
@@ -1389,8 +1434,10 @@ __device__ __forceinline__ uint64_t rol64(uint64_t x, uint32_t r)
 }
 __global__ void __launch_bounds__(256) k_windows(const __grid_constant__ K3Args A)
 {
+    if (*A.err & ERR_CAP) return;
+    const uint64_t n_min = *A.n_min_p;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_min; g += stride) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_min; g += stride) {
         const uint4 first = A.mins[g];
         const uint32_t rid = first.w;
         const uint64_t c = g - A.min_off[rid];             // window index inside the sequence == offset
@@ -1440,15 +1487,17 @@ __global__ void __launch_bounds__(256) k_windows_w(const __grid_constant__ K3Arg
     constexpr uint32_t OUT = 32 - (K - 1);                  // windows emitted per warp pass
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t n_pass = (A.n_min + OUT - 1) / OUT;
+    if (*A.err & ERR_CAP) return;
+    const uint64_t n_min = *A.n_min_p;
+    const uint64_t n_pass = (n_min + OUT - 1) / OUT;
     for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_pass; p += nwarps) {
         const uint64_t g = p * OUT + lane;
         uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-        if (g < A.n_min) rec = A.mins[g];
+        if (g < n_min) rec = A.mins[g];
         uint64_t f = 0, r = 0;
         WindowFold<K, 0>::run(mix32(rec.x), f, r);
         const uint32_t end = K > 1 ? __shfl_down_sync(0xffffffffu, rec.z, K - 1) : rec.z;
-        if (lane < OUT && g < A.n_min) {
+        if (lane < OUT && g < n_min) {
             const uint32_t rid = rec.w;
             const uint64_t c = g - A.min_off[rid];          // window index inside the sequence == offset
             const uint64_t k0 = A.km_off[rid];
@@ -1474,6 +1523,8 @@ template <int K>
 __global__ void __launch_bounds__(256) k_windows_t(const __grid_constant__ K3TArgs A)
 {
     constexpr uint32_t OUT = 32 - (K - 1);
+    if (*A.W.err & ERR_CAP) return;
+    const uint64_t n_min = *A.W.n_min_p;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < A.n_tiles; t += nwarps) {
@@ -1485,7 +1536,7 @@ __global__ void __launch_bounds__(256) k_windows_t(const __grid_constant__ K3TAr
             uint4 rec = make_uint4(0u, 0u, 0u, 0u);
             if (j < h) {
                 rec = A.W.mins[ts.y + j];
-            } else if (j - h < (uint32_t)(K - 1) && ts.x + j < A.W.n_min) {
+            } else if (j - h < (uint32_t)(K - 1) && ts.x + j < n_min) {
                 const uint64_t m = ts.x + j;
                 const uint32_t t2 = tile_of_record(A.tile_src, A.n_tiles, m, t + 1);
                 const ulonglong2 ts2 = A.tile_src[t2];
