@@ -206,6 +206,32 @@ void s2k_bounds(double density, uint32_t *bound_scalar, uint32_t *bound_simd, ui
 int  s2k_host_alloc(size_t bytes, void **out);
 void s2k_host_free(void *p);
 
+/* ---- Consumer side: abundance of the distinct k-min-mer hashes of an item stream.
+ * rust-mdbg inserts the iterator's items into a concurrent map keyed by the k-min-mer hash (KminmerHash is equal/ordered by
+ * `hash` alone, src/kminmer.rs:181-203; "Dashmap level ... kminmer hash collision", src/lib.rs:256-258).  The device table
+ * does the same in HBM, so that only the distinct (hash, count, id of the first item carrying it) triples leave the GPU. */
+typedef struct s2k_count_result {
+    uint64_t n_distinct;
+    uint64_t n_items;                /* items counted: sum of count[] */
+    const uint64_t *hash;            /* [n_distinct] distinct k-min-mer hashes, in no particular order */
+    const uint32_t *count;           /* [n_distinct] occurrences */
+    const uint64_t *first;           /* [n_distinct] smallest item id among the occurrences (id = id_base + index into
+                                        d_hash, or d_id[index]): leads back to start / end / rev of that item */
+    int32_t location;                /* S2K_LOC_DEVICE */
+    int32_t reserved;
+} s2k_count_result;
+/* d_hash: n_items k-min-mer hashes on the device (e.g. s2k_result.hash of s2k_run_device); d_id: their ids or NULL.
+ * Buffers of the result belong to the context and stay valid until its next s2k_count_device call. */
+int s2k_count_device(s2k_ctx *ctx, const uint64_t *d_hash, const uint64_t *d_id, uint64_t n_items, uint64_t id_base,
+                     void *stream, s2k_count_result *out);
+/* Several GPUs: every distinct hash is counted by rank s2k_count_part(hash, n_parts).  Buckets the items by that rank:
+ * d_out_hash / d_out_id [n_items] receive the items of part 0, then part 1, ...; part_counts[n_parts] (HOST) their sizes --
+ * the send buffers and split sizes of an all-to-all (NCCL), after which every rank calls s2k_count_device on what it
+ * received.  n_parts <= 64. */
+int s2k_count_partition_device(s2k_ctx *ctx, const uint64_t *d_hash, uint64_t n_items, uint64_t id_base, uint32_t n_parts,
+                               uint64_t *part_counts, uint64_t *d_out_hash, uint64_t *d_out_id, void *stream);
+uint32_t s2k_count_part(uint64_t hash, uint32_t n_parts);
+
 /* Diagnostics. */
 const char *s2k_last_error(const s2k_ctx *ctx);
 const char *s2k_strerror(int status);

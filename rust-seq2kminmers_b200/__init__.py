@@ -74,6 +74,11 @@ class _RleResult(C.Structure):
                 ("hpc_off", C.c_void_p), ("location", C.c_int32), ("reserved", C.c_int32)]
 
 
+class _CountResult(C.Structure):
+    _fields_ = [("n_distinct", C.c_uint64), ("n_items", C.c_uint64), ("hash", C.c_void_p), ("count", C.c_void_p),
+                ("first", C.c_void_p), ("location", C.c_int32), ("reserved", C.c_int32)]
+
+
 MINIMIZER_DTYPE = np.dtype([("hash", "<u4"), ("start", "<u4"), ("end", "<u4"), ("seq", "<u4")])
 
 # every symbol include/seq2kminmers.h declares
@@ -82,7 +87,7 @@ ABI_SYMBOLS = (
     "s2k_bounds", "s2k_host_alloc", "s2k_host_free", "s2k_last_error", "s2k_strerror", "s2k_abi_version",
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
     "s2k_ctx_set_slab_bytes", "s2k_run_fastx", "s2k_last_fastx", "s2k_ctx_set_transport",
-    "s2k_last_transport", "s2k_run_packed2", "s2k_pack2",
+    "s2k_last_transport", "s2k_run_packed2", "s2k_pack2", "s2k_count_device", "s2k_count_partition_device", "s2k_count_part",
 )
 
 
@@ -143,6 +148,12 @@ class Library:
         L.s2k_synth_device.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
         L.s2k_last_kernel_ms.restype = C.c_int
         L.s2k_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+        L.s2k_count_device.restype = C.c_int
+        L.s2k_count_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, C.POINTER(_CountResult)]
+        L.s2k_count_partition_device.restype = C.c_int
+        L.s2k_count_partition_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp, vp]
+        L.s2k_count_part.restype = C.c_uint32
+        L.s2k_count_part.argtypes = [C.c_uint64, C.c_uint32]
 
 
 _default: Optional[Library] = None
@@ -342,6 +353,23 @@ class Context:
                               f(_view(r.km_off, n + 1, np.uint64)), f(_view(r.min_off, n + 1, np.uint64)),
                               f(_view(r.min_cnt, n, np.uint32)), int(r.n_minimizers), None)
         return batch, f(_view(pb.value, int(nb.value), np.uint8)), f(_view(po.value, n + 1, np.uint64))
+
+    def count_device(self, d_hash_ptr: int, n_items: int, d_id_ptr: int = 0, id_base: int = 0, stream: int = 0) -> _CountResult:
+        """s2k_count_device: abundance of the distinct k-min-mer hashes of a device-resident item stream (the consumer side,
+        rust-mdbg's map keyed by KminmerHash).  Returns the ctypes result (device pointers: hash u64, count u32, first u64)."""
+        r = _CountResult()
+        self._check(self.lib.c.s2k_count_device(self.h, C.c_void_p(d_hash_ptr), C.c_void_p(d_id_ptr or None), int(n_items),
+                                                int(id_base), C.c_void_p(stream), C.byref(r)))
+        return r
+
+    def count_partition_device(self, d_hash_ptr: int, n_items: int, id_base: int, n_parts: int, d_out_hash_ptr: int,
+                               d_out_id_ptr: int, stream: int = 0) -> np.ndarray:
+        """s2k_count_partition_device: items bucketed by the rank that counts their hash; returns the bucket sizes."""
+        counts = np.zeros(int(n_parts), dtype=np.uint64)
+        self._check(self.lib.c.s2k_count_partition_device(self.h, C.c_void_p(d_hash_ptr), int(n_items), int(id_base), int(n_parts),
+                                                          counts.ctypes.data, C.c_void_p(d_out_hash_ptr), C.c_void_p(d_out_id_ptr),
+                                                          C.c_void_p(stream)))
+        return counts
 
     def synth_device(self, seed: int, first: int, count: int, d_out_ptr: int, stream: int = 0):
         """Fill device memory with the synthetic base stream of SURVEY.md 8(d)."""

@@ -4,6 +4,7 @@
 // There is no CPU fallback: every entry point that computes anything launches CUDA kernels or fails.
 #include "../../include/seq2kminmers.h"
 #include "s2k_kernels.cuh"
+#include "s2k_count.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -89,6 +90,7 @@ struct s2k_ctx {
     // device buffers
     Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_min_loc, d_tile_pre, d_hpc_off, d_km_off, d_min_cnt;
     Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr, d_tmp, d_tile_info, d_tile_base, d_tile_src;
+    Buf d_ct_keys, d_ct_cnt, d_ct_first, d_ct_side, d_co_hash, d_co_cnt, d_co_first, h_ct_side;   // s2k_count_device
     // pinned host result buffers
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
     Timing tm;
@@ -632,7 +634,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     Buf *all[] = {&ctx->d_bases, &ctx->d_seq_off, &ctx->d_tile_lb, &ctx->d_status, &ctx->d_small, &ctx->d_mins,
                   &ctx->d_min_off, &ctx->d_min_loc, &ctx->d_tile_pre, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
-                  &ctx->d_end, &ctx->d_rev, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->d_tile_src, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
+                  &ctx->d_end, &ctx->d_rev, &ctx->d_ct_keys, &ctx->d_ct_cnt, &ctx->d_ct_first, &ctx->d_ct_side, &ctx->d_co_hash, &ctx->d_co_cnt, &ctx->d_co_first, &ctx->h_ct_side, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->d_tile_src, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in[2], &ctx->d_in_off[0], &ctx->d_in_off[1], &ctx->d_in_off[2],
                   &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_off_stage[2], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1], &ctx->d_pack[2],
@@ -676,6 +678,96 @@ int s2k_last_kernel_ms(const s2k_ctx *ctx, double *minimizer_ms, double *window_
 }
 
 uint64_t s2k_launch_count(const s2k_ctx *ctx) { return ctx ? ctx->launches : 0; }
+// ---------------------------------------------------------------------------------------------- consumer side: counting
+uint32_t s2k_count_part(uint64_t hash, uint32_t n_parts)
+{
+    uint64_t x = hash;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (uint32_t)(((x >> 32) * (uint64_t)n_parts) >> 32);
+}
+
+int s2k_count_device(s2k_ctx *ctx, const uint64_t *d_hash, const uint64_t *d_id, uint64_t n_items, uint64_t id_base,
+                     void *stream, s2k_count_result *out)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (!out || (n_items && !d_hash)) return fail(ctx, S2K_ERR_NULL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    std::memset(out, 0, sizeof(*out));
+    out->location = S2K_LOC_DEVICE;
+    int rc;
+    uint64_t capacity = 1024;                              // load factor <= 2/3 even if every hash is distinct
+    while (capacity * 2 < n_items * 3) capacity <<= 1;
+    if ((rc = ensure(ctx, ctx->d_ct_keys, capacity * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ct_cnt, capacity * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ct_first, capacity * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ct_side, 32, false))) return rc;
+    if ((rc = ensure(ctx, ctx->h_ct_side, 32, true))) return rc;
+    const uint64_t n_out = std::max<uint64_t>(n_items, 1);
+    if ((rc = ensure(ctx, ctx->d_co_hash, n_out * 8, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_co_cnt, n_out * 4, false))) return rc;
+    if ((rc = ensure(ctx, ctx->d_co_first, n_out * 8, false))) return rc;
+    CU(cudaMemsetAsync(ctx->d_ct_keys.p, 0xff, capacity * 8, st));
+    CU(cudaMemsetAsync(ctx->d_ct_first.p, 0xff, capacity * 8, st));
+    CU(cudaMemsetAsync(ctx->d_ct_cnt.p, 0, capacity * 4, st));
+    unsigned long long *side = ptr<unsigned long long>(ctx->d_ct_side);
+    CU(cudaMemsetAsync(side, 0, 32, st));
+    CU(cudaMemsetAsync(side + 1, 0xff, 8, st));
+    KCArgs A;
+    A.hash = d_hash; A.id = d_id; A.n_items = n_items; A.id_base = id_base;
+    A.keys = ptr<unsigned long long>(ctx->d_ct_keys); A.cnt = ptr<uint32_t>(ctx->d_ct_cnt);
+    A.first = ptr<unsigned long long>(ctx->d_ct_first); A.mask = capacity - 1; A.side = side;
+    const int g1 = (int)std::min<uint64_t>((n_items + 255) / 256 + 1, (uint64_t)ctx->sm_count * 16);
+    S2K_LAUNCH(k_count_insert, g1, 256, 0, st, false, A);
+    KCOut O;
+    O.keys = A.keys; O.cnt = A.cnt; O.first = A.first; O.capacity = capacity; O.side = side;
+    O.out_hash = ptr<uint64_t>(ctx->d_co_hash); O.out_cnt = ptr<uint32_t>(ctx->d_co_cnt); O.out_first = ptr<uint64_t>(ctx->d_co_first);
+    const int g2 = (int)std::min<uint64_t>((capacity + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    S2K_LAUNCH(k_count_compact, g2, 256, 0, st, false, O);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(ctx->h_ct_side.p, side, 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out->n_distinct = ptr<uint64_t>(ctx->h_ct_side)[2];
+    out->n_items = n_items;
+    out->hash = ptr<uint64_t>(ctx->d_co_hash);
+    out->count = ptr<uint32_t>(ctx->d_co_cnt);
+    out->first = ptr<uint64_t>(ctx->d_co_first);
+    return S2K_OK;
+}
+
+int s2k_count_partition_device(s2k_ctx *ctx, const uint64_t *d_hash, uint64_t n_items, uint64_t id_base, uint32_t n_parts,
+                               uint64_t *part_counts, uint64_t *d_out_hash, uint64_t *d_out_id, void *stream)
+{
+    if (!ctx) return S2K_ERR_NULL;
+    if (!part_counts || (n_items && (!d_hash || !d_out_hash || !d_out_id))) return fail(ctx, S2K_ERR_NULL, "null argument");
+    if (n_parts == 0 || n_parts > (uint32_t)CT_MAX_PARTS) return fail(ctx, S2K_ERR_BAD_PARAM, "n_parts must be 1..64");
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_ct_side, 8 * 2 * CT_MAX_PARTS, false))) return rc;
+    if ((rc = ensure(ctx, ctx->h_ct_side, 8 * 2 * CT_MAX_PARTS, true))) return rc;
+    unsigned long long *cnt = ptr<unsigned long long>(ctx->d_ct_side), *cur = cnt + CT_MAX_PARTS;
+    uint64_t *h = ptr<uint64_t>(ctx->h_ct_side);
+    CU(cudaMemsetAsync(cnt, 0, 8 * CT_MAX_PARTS, st));
+    const int g = (int)std::min<uint64_t>((n_items + 255) / 256 + 1, (uint64_t)ctx->sm_count * 8);
+    S2K_LAUNCH(k_count_hist, g, 256, 0, st, false, d_hash, n_items, n_parts, cnt);
+    CU(cudaMemcpyAsync(h, cnt, 8 * CT_MAX_PARTS, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t acc = 0;
+    for (uint32_t p = 0; p < n_parts; ++p) { part_counts[p] = h[p]; h[CT_MAX_PARTS + p] = acc; acc += h[p]; }
+    CU(cudaMemcpyAsync(cur, h + CT_MAX_PARTS, 8 * n_parts, cudaMemcpyHostToDevice, st));
+    S2K_LAUNCH(k_count_scatter, g, 256, 0, st, false, d_hash, n_items, id_base, n_parts, cur, d_out_hash, d_out_id);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    CU(cudaStreamSynchronize(st));
+    return S2K_OK;
+}
+
 #if defined(S2K_PHASE_CLOCKS) && !defined(S2K_EMU)
 // debug builds only (tools/phase_clocks.py): cycles thread 0 of every CTA spent per phase of k_minimizers since the last call
 extern "C" int s2k_debug_phase_clocks(unsigned long long *out16)
