@@ -42,9 +42,10 @@ def _fetch(S, r, n, device):
     return h[o], c[o], f[o]
 
 
-def count_distributed(ctx, d_hash_ptr: int, n_items: int, id_base: int, device, group=None, stream: int = 0):
+def count_distributed(ctx, d_hash_ptr: int, n_items: int, id_base: int, device, group=None, stream: int = 0, fetch: bool = True):
     """All ranks of the default (or given) process group call this with their own items.  Every distinct hash ends up on
-    exactly one rank; returns this rank's (hash, count, first) sorted by hash, plus the seconds spent in the exchange."""
+    exactly one rank; returns this rank's (hash, count, first) sorted by hash, plus the seconds spent in the exchange.
+    fetch=False: the table stays on the device -- returns (s2k_count_result, None, None, seconds)."""
     import importlib
     import time
     import torch
@@ -69,6 +70,8 @@ def count_distributed(ctx, d_hash_ptr: int, n_items: int, id_base: int, device, 
         torch.cuda.synchronize(dev)
     t_exchange = time.perf_counter() - t0
     r = ctx.count_device(recv_h.data_ptr(), n_recv, recv_i.data_ptr(), 0, stream)
+    if not fetch:
+        return r, None, None, t_exchange
     h, c, f = _fetch(S, r, int(r.n_distinct), None if dev.type == "cpu" else dev)
     return h, c, f, t_exchange
 

@@ -46,8 +46,8 @@ for rep in range(3):
         r = ctx.count_device(res.hash, n_items, 0, 0, stream)
         nd, t_x = int(r.n_distinct), 0.0
     else:
-        h, c, f, t_x = C.count_distributed(ctx, res.hash, n_items, first, dev)
-        nd = len(h)
+        r, _, _, t_x = C.count_distributed(ctx, res.hash, n_items, first, dev, fetch=False)
+        nd = int(r.n_distinct)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 t = torch.tensor([dt, t_x], dtype=torch.float64, device=dev)
@@ -59,7 +59,7 @@ if rank == 0:
     out.update(seconds=float(t[0]), exchange_seconds=float(t[1]), distinct=int(s[0]), items=int(s[1]),
                items_per_s=int(s[1]) / float(t[0]),
                note="count_device = insert + compact kernels (last of 3 repeats); multi-GPU adds bucket-by-hash, the NCCL "
-                    "all-to-all of (hash, id) pairs, and a host copy of this rank's distinct entries")
+                    "all-to-all of (hash, id) pairs; the table stays on the device")
     print(json.dumps(out))
 if world > 1:
     dist.destroy_process_group()
