@@ -112,6 +112,9 @@ typedef struct s2k_ctx s2k_ctx;
 #define S2K_RLE_SCALAR_RULE 4u  /* s2k_encode_rle: the rule of the scalar `encode_rle` (src/hpc.rs:14): a repeated byte is
                                    dropped only if it is one of "ACTGactgNn"; default = `encode_rle_simd` / `hpc`
                                    (src/hpc.rs:33,86-95): every repeated byte is dropped */
+#define S2K_FASTX_KEEP_BASES 32u /* s2k_run_fastx: keep the parsed bases as one ASCII batch on the host (s2k_last_fastx returns
+                                   it).  Without it large files stream through the device slab by slab and are never
+                                   materialised (s2k_last_fastx then returns NULL for the bases; offsets are always kept) */
 #define S2K_DEBUG_TINY_CAP  8u  /* tests only: start with room for 1000 minimizers so that the grow-and-rerun path runs */
 #define S2K_NO_MINIMIZER_STREAM 16u /* s2k_run_device: do not materialise the ordered minimizer stream (result.minimizers
                                    is NULL; items, km_off, min_off, min_cnt are unchanged).  The records stay where the
@@ -143,9 +146,14 @@ int s2k_ctx_set_slab_bytes(s2k_ctx *ctx, uint64_t bytes);
 
 /* Host ingest + run: the loop of the reference's driver, `parallel_fastx(&filename, nb_threads, task)` with
  * `task = |seq, id| KminmersIterator::new(seq, l, k, density, mode)` (src/main.rs:65-79; rust-parallelfastx is an
- * external crate).  `path` is a plain-text FASTA (multi-line allowed) or 4-line FASTQ file; it is mapped and parsed on
- * nb_threads host threads straight into pinned memory (line ends stripped, records in file order), then goes through
- * s2k_run.  s2k_last_fastx returns the parsed batch (pointers owned by the context, valid until the next fastx call). */
+ * external crate).  `path` is a plain-text FASTA (multi-line allowed) or 4-line FASTQ file; it is mapped and indexed on
+ * nb_threads host threads (records in file order).  Files larger than 1.5 slabs whose records have lines of one width
+ * (any FASTQ, the usual FASTA) STREAM: the host threads gather slab i+1 from the mapping, line ends stripped, and pack it
+ * to 2 bits per base straight into pinned staging while slab i is on the device -- the file is read once and never
+ * exists as one batch on the host.  Other files (small, uneven lines) and callers that set S2K_FASTX_KEEP_BASES get
+ * the records copied into one pinned ASCII batch that goes through s2k_run.  Results are identical either way.
+ * s2k_last_fastx returns the parsed batch (pointers owned by the context, valid until the next fastx call; `bases` is
+ * NULL after a streamed run). */
 int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_params *params, s2k_result *out);
 int s2k_last_fastx(const s2k_ctx *ctx, uint64_t *n_seqs, uint64_t *n_bases, const uint8_t **bases, const uint64_t **seq_off);
 

@@ -337,13 +337,18 @@ class Context:
         return r
 
     def run_fastx(self, path, nb_threads: int, l: int, k: int, density: float, mode: HashMode,
-                  variant: HashVariant = HashVariant.NT1_32, copy: bool = True):
+                  variant: HashVariant = HashVariant.NT1_32, copy: bool = True, keep_bases: bool = True):
         """parallel_fastx(path, nb_threads, |seq, id| KminmersIterator::new(seq, l, k, density, mode)) of src/main.rs:65-79.
-        Returns (KminmersBatch, bases u8[], seq_off u64[]) -- the parsed records in file order and their k-min-mers."""
+        Returns (KminmersBatch, bases u8[], seq_off u64[]) -- the parsed records in file order and their k-min-mers.
+        keep_bases=False: large files stream through the device slab by slab (packed on the fly, never materialised on the
+        host); `bases` is then None."""
         p = _Params(int(l), int(k), float(density), int(mode), int(variant))
         r = _Result()
-        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 0))
-        self._check(self.lib.c.s2k_run_fastx(self.h, str(path).encode(), int(nb_threads), C.byref(p), C.byref(r)))
+        self._check(self.lib.c.s2k_ctx_set_flags(self.h, 32 if keep_bases else 0))     # S2K_FASTX_KEEP_BASES
+        try:
+            self._check(self.lib.c.s2k_run_fastx(self.h, str(path).encode(), int(nb_threads), C.byref(p), C.byref(r)))
+        finally:
+            self.lib.c.s2k_ctx_set_flags(self.h, 0)
         ns, nb, pb, po = C.c_uint64(), C.c_uint64(), C.c_void_p(), C.c_void_p()
         self._check(self.lib.c.s2k_last_fastx(self.h, C.byref(ns), C.byref(nb), C.byref(pb), C.byref(po)))
         f = (lambda a: a.copy()) if copy else (lambda a: a)
@@ -352,7 +357,8 @@ class Context:
                               f(_view(r.end, r.n_items, np.uint32)), f(_view(r.rev, r.n_items, np.uint8)),
                               f(_view(r.km_off, n + 1, np.uint64)), f(_view(r.min_off, n + 1, np.uint64)),
                               f(_view(r.min_cnt, n, np.uint32)), int(r.n_minimizers), None)
-        return batch, f(_view(pb.value, int(nb.value), np.uint8)), f(_view(po.value, n + 1, np.uint64))
+        bases = f(_view(pb.value, int(nb.value), np.uint8)) if pb.value else None      # None: the file was streamed
+        return batch, bases, f(_view(po.value, n + 1, np.uint64))
 
     def count_device(self, d_hash_ptr: int, n_items: int, d_id_ptr: int = 0, id_base: int = 0, stream: int = 0) -> _CountResult:
         """s2k_count_device: abundance of the distinct k-min-mer hashes of a device-resident item stream (the consumer side,

@@ -109,7 +109,9 @@ struct s2k_ctx {
     double pack_ratio = 0.7;        // share of slabs that travel packed (the rest keep PCIe busy with plain ASCII)
     uint64_t tr_h2d_bytes = 0, tr_packed = 0, tr_plain = 0;   // last s2k_run: bytes copied to the device, slabs by kind
     Buf h_fx_bases, h_fx_off;       // s2k_run_fastx: parsed file in pinned memory
+    Buf h_ascii[3];                 // ... slabs that cannot travel packed, gathered as ASCII
     uint64_t fx_n_seqs = 0, fx_n_bases = 0;
+    bool fx_have_bases = false;     // the last s2k_run_fastx materialised the parsed bases (small file, or S2K_FASTX_KEEP_BASES)
 };
 
 namespace {
@@ -637,7 +639,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
                   &ctx->d_end, &ctx->d_rev, &ctx->d_ct_keys, &ctx->d_ct_cnt, &ctx->d_ct_first, &ctx->d_ct_side, &ctx->d_co_hash, &ctx->d_co_cnt, &ctx->d_co_first, &ctx->h_ct_side, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->d_tile_src, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in[2], &ctx->d_in_off[0], &ctx->d_in_off[1], &ctx->d_in_off[2],
-                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_off_stage[2], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->d_pack[0], &ctx->d_pack[1], &ctx->d_pack[2],
+                  &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_off_stage[2], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->h_ascii[0], &ctx->h_ascii[1], &ctx->h_ascii[2], &ctx->d_pack[0], &ctx->d_pack[1], &ctx->d_pack[2],
                   &ctx->h_pack[0], &ctx->h_pack[1], &ctx->h_pack[2]};
     for (Buf *b : all) release(*b);
     if (ctx->tm.created) {
@@ -883,11 +885,17 @@ struct Slab {
 };
 // packed_in: `bases` is the caller's 2-bit packed batch (s2k_run_packed2) -- slabs are copied as they are and unpacked
 // on the device; the host packers stay idle.
+// fx: the bases come from a mapped FASTA/FASTQ file (s2k_run_fastx; `bases` is null): EVERY slab is gathered from the file
+// and packed to 2 bits by the host threads straight into the pinned staging ring -- file bytes are read once, a quarter
+// of a byte per base is written -- while earlier slabs are on the device; a slab holding a byte other than upper-case
+// A/C/G/T is gathered as ASCII instead.
 static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off, uint64_t n_seqs, const Plan &P,
-                         uint64_t slab_bytes, uint64_t overlap, int &overlap_short, s2k_result *out, bool packed_in)
+                         uint64_t slab_bytes, uint64_t overlap, int &overlap_short, s2k_result *out, bool packed_in,
+                         const FxSource *fx = nullptr, int fx_threads = 0)
 {
     int rc;
     auto base_at = [&](uint64_t i) -> uint8_t {             // equality of bases is all the host ever asks
+        if (fx) return fx_base_at(*fx, i);
         return packed_in ? (uint8_t)((bases[i >> 2] >> (2 * (i & 3))) & 3u) : bases[i];
     };
     overlap_short = 0;                                     // 1: redo with a longer overlap, 2: only the one-shot run will do
@@ -976,17 +984,19 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
     // buffers), copied (a quarter of the bytes) and unpacked on the device; the other slabs go as plain ASCII so that
     // PCIe and the packers work at the same time.  A slab with any byte outside upper-case ACGT goes as ASCII.
     int T = ctx->host_threads > 0 ? ctx->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() * 3 / 4));
-    const bool can_pack = !packed_in && host_has_avx512() && ctx->pack_ratio > 0.0 && n_slabs >= 3;
+    if (fx && fx_threads > 0) T = fx_threads;
+    const bool can_pack = fx || (!packed_in && host_has_avx512() && ctx->pack_ratio > 0.0 && n_slabs >= 3);
     std::vector<int> ps_of(n_slabs, -1);
     std::vector<size_t> packed_slabs;
     if (can_pack) {
         double acc = 0.0;
         for (size_t s = 0; s < n_slabs; ++s) {
-            acc += std::min(1.0, ctx->pack_ratio);
+            acc += fx ? 1.0 : std::min(1.0, ctx->pack_ratio);
             if (acc >= 1.0 - 1e-9) { acc -= 1.0; ps_of[s] = (int)packed_slabs.size(); packed_slabs.push_back(s); }
         }
     }
     const size_t np = packed_slabs.size();
+    if (fx) for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->h_ascii[i], 256, true))) return rc;   // grown on demand
     if (np) {
         for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->d_pack[i], max_b / 4 + 64, false))) return rc;
         for (int i = 0; i < 3; ++i) if ((rc = ensure(ctx, ctx->h_pack[i], max_b / 4 + 64, true))) return rc;
@@ -1015,7 +1025,17 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
                     const uint64_t b0 = slabs[sl].b0, nb = slabs[sl].hi - b0;
                     const uint64_t chunk = ((nb + T - 1) / T + 63) & ~uint64_t(63);
                     const uint64_t lo = std::min<uint64_t>(nb, chunk * wi), hi = std::min<uint64_t>(nb, lo + chunk);
-                    if (hi > lo) pk_bad[ps].fetch_add(pack2_range(bases + b0, ptr<uint8_t>(ctx->h_pack[ps % 3]), lo, hi));
+                    if (hi > lo && fx) {
+                        // gather 16 K bases at a time into a cache-resident block (line ends and headers drop out), pack it
+                        uint8_t blk[16384];
+                        uint64_t bad = 0;
+                        for (uint64_t q = lo; q < hi; q += sizeof(blk)) {
+                            const uint64_t e = std::min<uint64_t>(hi, q + sizeof(blk));
+                            fx_gather(*fx, b0 + q, b0 + e, blk);
+                            bad += pack2_range(blk, ptr<uint8_t>(ctx->h_pack[ps % 3]) + (q >> 2), 0, e - q);
+                        }
+                        pk_bad[ps].fetch_add(bad);
+                    } else if (hi > lo) pk_bad[ps].fetch_add(pack2_range(bases + b0, ptr<uint8_t>(ctx->h_pack[ps % 3]), lo, hi));
                     pk_done[ps].fetch_add(1, std::memory_order_release);
                 }
             });
@@ -1061,6 +1081,21 @@ static int run_pipelined(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq
             const int g = (int)std::min<uint64_t>((nb / 16 + 256) / 256, (uint64_t)ctx->sm_count * 8);
             S2K_LAUNCH(k_unpack2, g, 256, 0, ctx->s_h2d, false, ptr<uint32_t>(ctx->d_pack[b]), nb, ptr<uint8_t>(ctx->d_in[b]), 0u);
             ctx->launches += 1;
+        } else if (fx) {                                                  // a byte outside ACGT: this slab travels as ASCII
+            if (ps >= 0) pk_state[ps] = 2;
+            CU(cudaEventSynchronize(ctx->ev_in[b]));                      // the copy of slab s-3 out of this staging buffer
+            if ((rc = ensure(ctx, ctx->h_ascii[b], nb + 64, true))) return rc;
+            {
+                std::vector<std::thread> th;
+                const uint64_t chunk = (nb + T - 1) / T;
+                for (int wi = 0; wi < T; ++wi)
+                    th.emplace_back([&, wi]() {
+                        const uint64_t lo = std::min<uint64_t>(nb, chunk * wi), hi = std::min<uint64_t>(nb, lo + chunk);
+                        fx_gather(*fx, L.b0 + lo, L.b0 + hi, ptr<uint8_t>(ctx->h_ascii[b]) + lo);
+                    });
+                for (auto &x : th) x.join();
+            }
+            if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, ctx->h_ascii[b].p, nb, cudaMemcpyHostToDevice, ctx->s_h2d));
         } else {
             if (ps >= 0) pk_state[ps] = 2;
             if (nb) CU(cudaMemcpyAsync(ctx->d_in[b].p, bases + L.b0, nb, cudaMemcpyHostToDevice, ctx->s_h2d));
@@ -1403,6 +1438,11 @@ int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_para
         return fail(ctx, S2K_ERR_IO, "not a FASTA/FASTQ file (first record must start with '>' or '@')");
     const bool fastq = first < f.n && f.p[first] == '@';
     const int T = (int)std::min<size_t>((size_t)nb_threads, std::max<size_t>(1, f.n >> 16));
+    const bool fx_timing = getenv("S2K_FASTX_TIMING") != nullptr;
+    const auto fx_t0 = std::chrono::steady_clock::now();
+    auto fx_lap = [&](const char *what) {
+        if (fx_timing) fprintf(stderr, "[s2k fastx] %-28s at %.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - fx_t0).count());
+    };
     std::vector<std::vector<FxRec>> recs((size_t)T);
     std::vector<uint64_t> nb((size_t)T, 0);
     {
@@ -1411,15 +1451,56 @@ int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_para
             th.emplace_back([&, t]() { fx_scan(f.p, f.n, f.n * (size_t)t / T, f.n * (size_t)(t + 1) / T, fastq, recs[t], nb[t]); });
         for (auto &x : th) x.join();
     }
+    fx_lap("records indexed");
     uint64_t n_seqs = 0, n_bases = 0;
     std::vector<uint64_t> seq_base((size_t)T), byte_base((size_t)T);
     for (int t = 0; t < T; ++t) { seq_base[t] = n_seqs; byte_base[t] = n_bases; n_seqs += recs[t].size(); n_bases += nb[t]; }
     int rc;
     CU(cudaSetDevice(ctx->device));
-    if ((rc = ensure(ctx, ctx->h_fx_bases, n_bases + 64, true))) return rc;
     if ((rc = ensure(ctx, ctx->h_fx_off, (n_seqs + 1) * 8, true))) return rc;
-    uint8_t *hb = ptr<uint8_t>(ctx->h_fx_bases);
     uint64_t *ho = ptr<uint64_t>(ctx->h_fx_off);
+    ctx->fx_n_seqs = n_seqs; ctx->fx_n_bases = n_bases; ctx->fx_have_bases = false;
+
+    // ---- streaming form: large files whose records are addressable in O(1) never exist as one ASCII batch on the host.
+    // The host threads gather and pack slab i+1 straight from the mapping while slab i is on the device (run_pipelined).
+    const uint64_t slab = ctx->slab_bytes ? ctx->slab_bytes : (256ull << 20);
+    bool addressable = true;
+    for (int t = 0; t < T && addressable; ++t)
+        for (const FxRec &r : recs[t]) if (r.n && r.width == 0) { addressable = false; break; }
+    const bool keep = (ctx->flags & S2K_FASTX_KEEP_BASES) != 0;
+    if (addressable && !keep && n_bases > slab + slab / 2) {
+        std::vector<FxRec> all;
+        all.reserve(n_seqs);
+        for (int t = 0; t < T; ++t) all.insert(all.end(), recs[t].begin(), recs[t].end());
+        uint64_t o = 0;
+        for (uint64_t i = 0; i < n_seqs; ++i) { ho[i] = o; o += all[i].n; }
+        ho[n_seqs] = n_bases;
+        Plan P;
+        if ((rc = make_plan(ctx, params, P)) != S2K_OK) return rc;
+        if ((rc = check_offsets(ctx, ho, n_seqs)) != S2K_OK) return rc;
+        ctx->err.clear();
+        FxSource src;
+        src.file = f.p; src.recs = all.data(); src.seq_off = ho; src.n_recs = n_seqs;
+        const double frac = std::max(1e-9, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+        uint64_t overlap = (uint64_t)std::min(4.0e9, 64.0 * (P.k + 8.0) / frac + 64.0 * P.l + 4096.0);
+        fx_lap("offsets built");
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            int too_short = 0;
+            rc = run_pipelined(ctx, nullptr, ho, n_seqs, P, slab, overlap, too_short, out, false, &src, nb_threads);
+            fx_lap("streamed through the device");
+            if (rc != S2K_OK || !too_short) {
+                if (rc != S2K_OK && ctx->pipe_ready) { cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_d2h); cudaStreamSynchronize(ctx->stream); }
+                return rc;
+            }
+            CU(cudaStreamSynchronize(ctx->s_h2d)); CU(cudaStreamSynchronize(ctx->s_d2h)); CU(cudaStreamSynchronize(ctx->stream));
+            if (too_short == 2) break;
+            overlap = std::min<uint64_t>(n_bases, overlap * 8);
+        }                                                  // a long sequence that defeats the piece logic: materialise it, below
+    }
+
+    // ---- materialised form: the records copied to one pinned ASCII batch (small files, uneven lines, or on request)
+    if ((rc = ensure(ctx, ctx->h_fx_bases, n_bases + 64, true))) return rc;
+    uint8_t *hb = ptr<uint8_t>(ctx->h_fx_bases);
     {
         std::vector<std::thread> th;
         for (int t = 0; t < T; ++t)
@@ -1430,7 +1511,7 @@ int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_para
         for (auto &x : th) x.join();
     }
     ho[n_seqs] = n_bases;
-    ctx->fx_n_seqs = n_seqs; ctx->fx_n_bases = n_bases;
+    ctx->fx_have_bases = true;
     return s2k_run(ctx, hb, ho, n_seqs, params, out);
 }
 
@@ -1439,7 +1520,7 @@ int s2k_last_fastx(const s2k_ctx *ctx, uint64_t *n_seqs, uint64_t *n_bases, cons
     if (!ctx) return S2K_ERR_NULL;
     if (n_seqs) *n_seqs = ctx->fx_n_seqs;
     if (n_bases) *n_bases = ctx->fx_n_bases;
-    if (bases) *bases = reinterpret_cast<const uint8_t *>(ctx->h_fx_bases.p);
+    if (bases) *bases = ctx->fx_have_bases ? reinterpret_cast<const uint8_t *>(ctx->h_fx_bases.p) : nullptr;
     if (seq_off) *seq_off = reinterpret_cast<const uint64_t *>(ctx->h_fx_off.p);
     return S2K_OK;
 }

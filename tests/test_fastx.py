@@ -45,6 +45,21 @@ def check(S, O, ctx, path, seqs, threads, mode=3):
     assert_batch_matches_oracle(O, batch, bases, so, 31, 5, 0.02, mode)
 
 
+def check_streamed(S, O, ctx, path, seqs, threads, mode=3, slab=6000):
+    """The same file through the streaming form (slabs gathered and packed from the mapping, keep_bases=False)."""
+    ctx.set_slab_bytes(slab)
+    try:
+        batch, bases, so = ctx.run_fastx(path, threads, 31, 5, 0.02, S.HashMode(mode), keep_bases=False)
+    finally:
+        ctx.set_slab_bytes(0)
+    want_so = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    want_so[1:] = np.cumsum([len(s) for s in seqs])
+    assert np.array_equal(so, want_so)
+    want_bases = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8)
+    assert_batch_matches_oracle(O, batch, want_bases, so, 31, 5, 0.02, mode)
+    return bases
+
+
 def _cases(batches, tmp_path, big):
     rng = batches.rng
     lens = [0, 1, 31, 32, 150, 150, 7000, 0, 20000, 59, 60, 61, 120] + list(rng.integers(0, 400, 300))
@@ -68,9 +83,12 @@ def _cases(batches, tmp_path, big):
 
 
 def test_fastx_ingest_emulated(S, O, emu_ctx, batches, tmp_path):
+    streamed = 0
     for path, seqs in _cases(batches, tmp_path, big=False):
         for threads in (1, 3):
             check(S, O, emu_ctx, path, seqs, threads)
+        streamed += check_streamed(S, O, emu_ctx, path, seqs, 3) is None
+    assert streamed >= 5                                   # blank.fa has lines of uneven width: materialised after all
     with pytest.raises(S.S2KError) as e:
         emu_ctx.run_fastx(tmp_path / "missing.fa", 2, 31, 5, 0.02, S.HashMode.Hpc)
     assert e.value.status == -8
@@ -87,6 +105,8 @@ def test_fastx_ingest_gpu(S, O, gpu_ctx, batches, tmp_path):
     for path, seqs in _cases(batches, tmp_path, big=True):
         for threads in (1, 8):
             check(S, O, gpu_ctx, path, seqs, threads)
+        check_streamed(S, O, gpu_ctx, path, seqs, 8, slab=200000)
+        check_streamed(S, O, gpu_ctx, path, seqs, 5, mode=1, slab=70000)      # long reads in pieces, scalar profile
 
 
 @pytest.mark.gpu
