@@ -128,6 +128,9 @@ struct Smem {
     uint2    xrm[64];                        // packed warm-up: what the 0..3 oldest codes of its first byte added (see hash_owners_packed)
     alignas(16) uint32_t pk[PKW];            // packed tiles: 2-bit class of every kept base, 16 per word, same index space as code[]
     uint32_t rare;                           // a thread met a rare class while packing: the tile is redone byte-wise
+    uint32_t tma_tile;                       // tile whose window a bulk copy is bringing into code[] (packed tiles leave
+    uint32_t code_raw;                       // code[] free), ~0u = none; code_raw: code[] holds raw bases, not class codes
+    alignas(8) unsigned long long mbar;      // completion barrier of the bulk copy
     alignas(16) uint8_t pre[16];             // stays ZC8: with l = 255 and owner space shifted 3 bases into the halo the
                                              // word-wise hash stage reads up to 4 bytes below code[0]
     uint8_t  code[XB + WIN + 128];           // 8*class of every kept base, index XB + (kept index in the window)
@@ -586,6 +589,33 @@ __device__ unsigned long long g_phase[16];
 #define PHASE(i)
 #define PHASE_FLUSH
 #endif
+#if !defined(S2K_EMU) && !defined(S2K_NO_TMA)
+#define S2K_TMA 1
+#endif
+// ---- 1-D bulk copy (TMA) of the next tile's window into shared memory, completion on an mbarrier.
+// One thread arms the barrier with the byte count and issues cp.async.bulk; the copy engine fetches the 16 KB while the
+// CTA hashes the current tile; at the next tile every thread waits on the barrier's phase and reads its pieces with
+// four conflict-free 16-byte shared loads instead of four global loads.
+#ifdef S2K_TMA
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic-proxy accesses of dst come first
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tS2K_MBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra S2K_MBAR_DONE;\n\t"
+                 "bra S2K_MBAR_WAIT;\n\tS2K_MBAR_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
 // S3a of k_minimizers: this thread's four pieces of 16 raw bases (piece 32*j + lane of its warp's 2048 bases).
 __device__ __forceinline__ void load_pieces(const K1Args &A, int64_t W0, int xw, bool full, uint32_t (&w)[16])
 {
@@ -668,6 +698,16 @@ __device__ __forceinline__ uint32_t compact_packed(Smem &S, smem_tab_t xft, cons
     return seen >= 128u ? 0x80u : 0u;
 }
 
+// A tile in byte form after bulk copies have used code[] as their landing buffer: raw bases are not class codes (the
+// hash stage forms table offsets from whatever lies around the kept bases), so the array is reset first.  Rare.
+__device__ __forceinline__ void reset_codes(Smem &S)
+{
+    const uint32_t z = ZC8 * 0x01010101u;
+    for (int i = threadIdx.x; i < (int)(sizeof(S.code) / 16); i += NT) reinterpret_cast<uint4 *>(S.code)[i] = make_uint4(z, z, z, z);
+    __syncthreads();
+    if (threadIdx.x == 0) S.code_raw = 0u;
+}
+
 template <bool HPC, bool W31, bool DENSE>
 __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_constant__ K1Args A)
 {
@@ -701,7 +741,13 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         S.xrm[tid] = e;
     }
     for (int i = tid; i < PKW; i += NT) S.pk[i] = 0u;
-    if (tid == 0) S.rare = 0u;
+    if (tid == 0) {
+        S.rare = 0u; S.tma_tile = ~0u; S.code_raw = 0u;
+#ifdef S2K_TMA
+        mbar_init(&S.mbar, 1u);
+#endif
+    }
+    uint32_t tma_phase = 0;                                // parity of the next bulk copy to complete
     const smem_tab_t xft = smem_tab(S.xf);                 // S.lut lies 256 bytes below, S.lut2 256 above: one register
     if (tid == 0 && !smem_tab_ok(xft)) atomicOr(A.err, ERR_ALIGN);
     for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
@@ -746,6 +792,18 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const int xw = 2048 * warp + 16 * lane;            // window offset of this thread's piece of round 0
         const bool full = W0 >= 0 && W0 + (int64_t)WIN <= (int64_t)A.n_bases;      // uniform: the whole window is readable
         uint32_t w[16];
+#ifdef S2K_TMA
+        if (S.tma_tile == t) {                             // uniform: the bulk copy issued during the previous tile
+            mbar_wait(&S.mbar, tma_phase & 1u);
+            ++tma_phase;
+            const uint4 *src = reinterpret_cast<const uint4 *>(S.code + xw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 x = src[32 * j];
+                w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
+            }
+        } else
+#endif
         load_pieces(A, W0, xw, full, w);
 
         // ---- S2: sequence starts inside the tile (and the start of the sequence containing T0, if in the window)
@@ -863,6 +921,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         if (try_packed) {
             if (compact_packed(S, xft, w, k16, qj) & 0x80u) S.rare = 1u;
         } else {
+            if (S.code_raw) reset_codes(S);                // uniform; every thread read its pieces before the last barrier
             compact_bytes<HPC>(S, xft, w, k16, qj);
         }
         if (tid == 0) S.next[par ^ 1] = t_next;           // the ticket drawn at the top has long arrived
@@ -914,6 +973,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         __syncthreads();
         const bool packed = try_packed && S.rare == 0u;
         if (try_packed && !packed) {                       // uniform, rare: N, IUPAC, lower case ... -> byte form after all
+            if (S.code_raw) reset_codes(S);
             load_pieces(A, W0, xw, full, w);               // (the registers were not kept across the barrier)
             compact_bytes<HPC>(S, xft, w, k16, qj);
             __syncthreads();
@@ -921,9 +981,25 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         PHASE(4);
         const uint32_t tn = S.next[par ^ 1];
 #ifndef S2K_EMU
-        if (tn < A.n_tiles && tid < WIN / 128) {           // pull the next tile's bases into L2 while this one is hashed
-            const int64_t a = (int64_t)((uint64_t)tn * A.tile) - (int64_t)A.halo + 128 * tid;
-            if (a >= 0 && a < (int64_t)A.n_bases) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.bases + a));
+        {   // the next tile's window: one bulk copy (TMA) into code[], which a packed tile does not use; tiles in byte
+            // form (and windows that stick out of the batch) only pull the bases into L2
+            const int64_t wn = (int64_t)((uint64_t)tn * A.tile) - (int64_t)A.halo;
+#ifdef S2K_TMA
+            const bool bulk = packed && tn < A.n_tiles && wn >= 0 && wn + (int64_t)WIN <= (int64_t)A.n_bases;
+#else
+            const bool bulk = false;
+#endif
+#ifdef S2K_TMA
+            if (tid == 0) {
+                S.tma_tile = bulk ? tn : ~0u;
+                if (bulk) S.code_raw = 1u;
+                if (bulk) tma_load_1d(S.code, A.bases + wn, (uint32_t)WIN, &S.mbar);
+            }
+#endif
+            if (!bulk && tn < A.n_tiles && tid < WIN / 128) {
+                const int64_t a = wn + 128 * tid;
+                if (a >= 0 && a < (int64_t)A.n_bases) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.bases + a));
+            }
         }
 #endif
 
