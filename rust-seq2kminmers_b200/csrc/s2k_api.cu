@@ -279,21 +279,23 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     P.none = excl == 0;
     P.thr = P.none ? 0u : (uint32_t)(excl - 1);
     P.dense = (double)excl / (P.w31 ? 2147483648.0 : 4294967296.0) >= 0.0027;   // the canonical minimum doubles the rate
-    // base classes: 0..3 = A C G T, 4 = seed 0, 5 = seed 1
+    // base classes: 0..3 = A C T G (bits 1-2 of the ASCII byte: the packed compaction classifies with one AND),
+    // 4 = seed 0, 5 = seed 1.  SEED64 is in the order A C G T; the complement of seed s is seed 3 - s.
     const int w = P.w31 ? 31 : 32;
     uint32_t h[8] = {0}, rc[8] = {0};
+    static const int seed_of[4] = {0, 1, 3, 2};
     for (int b = 0; b < 4; ++b) {
-        h[b] = P.w31 ? (uint32_t)(SEED64[b] >> 33) : (uint32_t)SEED64[b];
-        rc[b] = P.w31 ? (uint32_t)(SEED64[3 - b] >> 33) : (uint32_t)SEED64[3 - b];
+        h[b] = P.w31 ? (uint32_t)(SEED64[seed_of[b]] >> 33) : (uint32_t)SEED64[seed_of[b]];
+        rc[b] = P.w31 ? (uint32_t)(SEED64[3 - seed_of[b]] >> 33) : (uint32_t)SEED64[3 - seed_of[b]];
     }
     h[5] = rc[5] = 1;
     static const uint8_t code_of[6] = {0, 8, 16, 24, 32, 40};     // see s2k_kernels.cuh (table layout)
     if (P.simd) {                                    // low nibble, src/nthash_avx512_32.rs:178-193
-        static const uint8_t nib[16] = {4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4};
+        static const uint8_t nib[16] = {4, 0, 4, 1, 2, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4};
         for (int i = 0; i < 256; ++i) P.lut[i] = code_of[nib[i & 15]];
     } else {                                         // src/nthash_hpc.rs:29-49
         for (int i = 0; i < 256; ++i) P.lut[i] = code_of[5];
-        P.lut['A'] = code_of[0]; P.lut['C'] = code_of[1]; P.lut['G'] = code_of[2]; P.lut['T'] = code_of[3];
+        P.lut['A'] = code_of[0]; P.lut['C'] = code_of[1]; P.lut['T'] = code_of[2]; P.lut['G'] = code_of[3];
         P.lut['N'] = code_of[4];
     }
     std::memset(P.xy, 0, sizeof(P.xy));
@@ -449,6 +451,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.err = reinterpret_cast<uint32_t *>(small + 5);
         A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
         A.tile = (uint32_t)tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
+        A.vmask = P.simd ? 0x0f0f0f0fu : 0xffffffffu; A.one = 1u;
         std::memcpy(A.cls_lut, P.lut, 256);
         std::memcpy(A.xy, P.xy, sizeof(P.xy));
         std::memcpy(A.xf, P.xf, sizeof(P.xf));

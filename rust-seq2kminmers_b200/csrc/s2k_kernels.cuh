@@ -48,18 +48,20 @@ constexpr int RAWPT = 64;           // raw bases per thread in the keep/compacti
 constexpr int WIN   = NT * RAWPT;   // raw bases staged per tile (left halo + tile)
 constexpr int NCHUNK = WIN / 32;    // 32-base chunks per window
 #ifndef S2K_CH
-#define S2K_CH 52
+#define S2K_CH 48
 #endif
 #ifndef S2K_HT
 #define S2K_HT S2K_NT
 #endif
-constexpr int CH    = S2K_CH;       // owner positions per hash thread.  CH/4 must be odd: the per-lane byte streams of a
-                                    // warp then fall into 32 different banks.  (52: 13 words; 100: 25 words.)
+constexpr int CH    = S2K_CH;       // owner positions per hash thread.  48 = three whole groups of 16 in the packed hash
+                                    // stage and 12 288 owners per pass: an HPC tile of 16 128 random bases keeps
+                                    // 12 096 +- 55, so one tile in 4 000 takes a second pass.  (With 52 the 9 % of idle
+                                    // owner slots cost 3 % of the kernel; the byte form, whose word streams want CH/4
+                                    // odd to avoid bank conflicts, only serves rare tiles.)
 constexpr int HT    = S2K_HT;       // threads of the CTA that hash (the others wait at the barrier meanwhile)
 constexpr int MW    = (CH + 63) / 64;   // 64-bit words of a thread's hit mask
-constexpr int CAP   = HT * CH;      // owners hashed per pass (a second pass covers tiles that compress badly); with
-                                    // ~75 % of bases kept, CAP >= 12.1 k covers a 16 128-base HPC tile in one pass
-static_assert(CH % 4 == 0 && ((CH / 4) & 1) == 1 && CH <= 128 && HT <= NT && 2 * CAP >= WIN, "hash geometry");
+constexpr int CAP   = HT * CH;      // owners hashed per pass (a second pass covers tiles that compress badly)
+static_assert(CH % 4 == 0 && CH <= 128 && HT <= NT && 2 * CAP >= WIN, "hash geometry");
 constexpr int XB    = 256;          // capacity of the left context, in kept (HPC) bases
 constexpr int FW    = (XB + WIN) / 32 + 2;   // words of the owner-space flag bitmaps
 constexpr int PKW   = (XB + WIN) / 16 + 8;   // words of the packed code array (a multiple of 4)
@@ -111,6 +113,8 @@ struct K1Args {
     uint64_t  n_seqs, n_bases;
     uint32_t  n_tiles, tile, halo;
     uint32_t  l, d, need, thr;
+    uint32_t  one;               // 1: a multiplier ptxas cannot fold keeps `x + bit` on the multiply-add pipe (one_r below)
+    uint32_t  vmask;             // packed compaction: bits of (canonical base ^ base) that make a base a rare class
     uint8_t   cls_lut[256];      // raw byte -> 8 * base class (classes 0..5)
     uint2     xy[XYN];           // byte offset 8*code(out)+code(in) -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
     uint2     xf[XFN];           // the same for ACGT x ACGT at byte offset 4*code(out)+code(in)
@@ -122,7 +126,7 @@ struct Smem {
     // with one PRMT instead of an extract + add (smem_splice below); k_minimizers checks the alignment once.
     alignas(256) uint8_t lut[256];           // raw byte -> 8 * base class
     alignas(256) uint2 xf[XFN];              // the 16 live entries cover the 32 banks once
-    alignas(256) uint8_t lut2[256];          // raw byte -> 2-bit class (A C G T = 0..3), 0x80 for the two rare classes
+    alignas(256) uint2 gm[32];               // packed compaction: keep nibble -> (gather multiplier, 2 * kept); 16 live entries
     alignas(128) uint2 x2[XFN];
     uint2    x4[256];                        // warm-up: (c0,c1,c2,c3) at c0 + 4*c1 + 16*c2 + 64*c3 advances the state by 4 bases
     uint2    xrm[64];                        // packed warm-up: what the 0..3 oldest codes of its first byte added (see hash_owners_packed)
@@ -156,7 +160,7 @@ struct Smem {
     uint16_t dirty[2][DIRTY_MAX];            // double-buffered by tile parity.  bit 15: f1/f2, else startw/shortw
     unsigned long long s0, rec0, rec_lim, cur;   // cur: records this CTA has appended to its region
 };
-static_assert(offsetof(Smem, lut) == 0 && offsetof(Smem, xf) == 256 && offsetof(Smem, lut2) == 512,
+static_assert(offsetof(Smem, lut) == 0 && offsetof(Smem, xf) == 256 && offsetof(Smem, gm) == 512,
               "k_minimizers derives the lut addresses from xf's");
 static_assert(offsetof(Smem, code) % 16 == 0 && offsetof(Smem, pk) % 16 == 0, "vector stores into code[] and pk[]");
 
@@ -449,7 +453,7 @@ __device__ __forceinline__ uint32_t hash_owners_words(const Smem &S, smem_tab_t 
 // added is taken out again with one look-up in xrm (the hash is XOR-linear in the bases).
 template <bool W31, bool DENSE>
 __device__ __forceinline__ void hash_owners_packed(const Smem &S, smem_tab_t xft, int E, int l, uint32_t thr, uint32_t *hs,
-                                                   unsigned long long (&mask)[MW])
+                                                   unsigned long long (&mask)[MW], uint32_t one)
 {
     constexpr int NG = (CH + 15) / 16;
     uint32_t mw[2 * MW];                                   // the hit mask as 32-bit words
@@ -521,7 +525,7 @@ __device__ __forceinline__ void hash_owners_packed(const Smem &S, smem_tab_t xft
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int i = 16 * g + 4 * r + t;
-                    if (hv[t] <= thr) { mw[i >> 5] = mad_u32(1u << (i & 31), 1u, mw[i >> 5]); hs[i] = hv[t]; }   // "|=" on the multiply-add pipe
+                    if (hv[t] <= thr) { mw[i >> 5] = mad_u32(one, 1u << (i & 31), mw[i >> 5]); hs[i] = hv[t]; }   // "|=" on the multiply-add pipe
                 }
             }
         }
@@ -664,38 +668,49 @@ __device__ __forceinline__ void compact_bytes(Smem &S, smem_tab_t xft, const uin
         }
     }
 }
-// S4, packed form: the 2-bit classes of a piece's kept bases are gathered in ONE register (bases visited from last to
-// first, acc = 4*acc + class: the first kept base ends up in the low bits) and OR-ed into the packed array with at most
-// two shared-memory atomics per piece -- 8 per thread where the byte form issues 64 conflicting byte stores.
-// Returns the OR of the look-ups: bit 7 set = a rare class was met (the caller redoes the tile in byte form).
-__device__ __forceinline__ uint32_t compact_packed(Smem &S, smem_tab_t xft, const uint32_t (&w)[16], const uint32_t (&k16)[4],
-                                                   const uint32_t (&qj)[4])
+// S4, packed form, all arithmetic (no look-up per base).  Per word of four raw bases:
+//   class    V = x & 0x06060606: bits 1-2 of an ASCII base are its class in the order A C T G = 0 1 2 3 (the class
+//            numbering of every table; it also is the 2-bit transport format)
+//   validity the low three bits of a base index an 8-entry byte table held in two registers (PRMT with a data-dependent
+//            selector is a 4-way table look-up): the canonical byte of that index, compared with the base itself.  The
+//            differences are OR-ed up and tested once per thread against vmask (0xff per byte in the scalar profile:
+//            exactly A C G T; 0x0f in the nibble profile: the low nibble decides, src/nthash_avx512_32.rs:178-193).
+//            A set bit = some base of a rare class: the tile is redone in byte form.
+//   gather   V * M[keep nibble] (low 32 bits) holds the classes of the kept bases of the word in its TOP 2*kept bits:
+//            the multiplier has one term per kept base j, 2^(31 - 2*kept + 2*rank(j) - 8j), which moves class j to bit
+//            32 - 2*kept + 2*rank(j); the other partial products fall off the top or below the field, no two on the
+//            same bits (so no carry).  A funnel shift pushes the field into the accumulator from below, last word
+//            first.
+// Nine ALU instructions and one multiply per word; two shared-memory atomics per piece.
+__device__ __forceinline__ uint32_t compact_packed(Smem &S, const uint32_t (&w)[16], const uint32_t (&k16)[4],
+                                                   const uint32_t (&qj)[4], uint32_t vmask)
 {
-    smem_tab_t t2 = xft + 256;                             // S.lut2
-#ifndef S2K_EMU
-    asm volatile("" : "+r"(t2));                           // one register for the whole loop (else re-derived per base)
-#endif
-    uint32_t seen = 0;
+    const uint8_t *gm = reinterpret_cast<const uint8_t *>(S.gm);
+    uint32_t bad = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        // acc gathers the classes; sum adds the look-ups up on the multiply-add pipe (the integer ALU is the busiest
-        // unit of this kernel): 16 classes sum to at most 48, a rare class (0x80) lifts the sum to 128 or more
-        uint32_t acc = 0, sum = 0;
+        uint32_t acc = 0;
 #pragma unroll
-        for (int b = 15; b >= 0; --b) {
-            if ((k16[j] >> b) & 1u) {
-                const uint32_t v = tab_u8(t2, w[4 * j + (b >> 2)], b & 3);
-                acc = acc * 4u + v;
-                sum = mad_u32(v, 1u, sum);
-            }
+        for (int i = 3; i >= 0; --i) {                     // last word first: the first kept base ends up in the low bits
+            const uint32_t x = w[4 * j + i];
+            const uint32_t y = x & 0x07070707u;
+            const uint32_t sel = y + (y >> 12);                                    // nibbles: y0 y2 y1 y3
+            uint32_t canon;
+#ifdef S2K_EMU
+            canon = __byte_perm(0x43014101u, 0x47000054u, sel);
+#else
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(canon) : "r"(0x43014101u), "r"(0x47000054u), "r"(sel));
+#endif
+            bad |= canon ^ __byte_perm(x, 0u, 0x3120u);
+            const uint2 e = *reinterpret_cast<const uint2 *>(gm + (((k16[j] << 3) >> (4 * i)) & 0x78u));
+            acc = __funnelshift_l((x & 0x06060606u) * e.x, acc, e.y);
         }
-        seen |= sum;
         const uint32_t p0 = (uint32_t)XB + qj[j], sh = 2u * (p0 & 15u);
         const uint32_t lo = acc << sh, hi = __funnelshift_l(acc, 0u, sh);
         if (lo) atomicOr(&S.pk[p0 >> 4], lo);
         if (hi) atomicOr(&S.pk[(p0 >> 4) + 1], hi);
     }
-    return seen >= 128u ? 0x80u : 0u;
+    return bad & vmask;
 }
 
 // A tile in byte form after bulk copies have used code[] as their landing buffer: raw bases are not class codes (the
@@ -729,7 +744,13 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const uint2 a = A.x2[4 * (i & 3) + ((i >> 2) & 3)], b = A.x2[4 * ((i >> 4) & 3) + (i >> 6)];
         S.x4[i] = make_uint2(rol2<W31>(a.x) ^ b.x, ror2<W31>(a.y) ^ b.y);
     }
-    for (int i = tid; i < 256; i += NT) { const uint32_t c = A.cls_lut[i]; S.lut2[i] = (uint8_t)(c < (uint32_t)ZC8 ? c >> 3 : 0x80u); }
+    if (tid < 16) {                                        // gm: see compact_packed
+        const int wd = 2 * __popc((uint32_t)tid);
+        uint32_t m = 0, r = 0;
+        for (int j = 0; j < 4; ++j)
+            if ((tid >> j) & 1) { m |= 1u << (31 - wd + 2 * (int)r - 8 * j); ++r; }
+        S.gm[tid] = make_uint2(m, (uint32_t)wd);
+    }
     if (tid < 64) {                                        // xrm: see hash_owners_packed (A.xy[32 + c] = (h[c], rol(rc[c], l-1)))
         const int n = (int)A.l - 1, nb = (n + 3) >> 2, sur = 4 * nb - n;
         uint2 e = make_uint2(0u, 0u);
@@ -748,7 +769,11 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 #endif
     }
     uint32_t tma_phase = 0;                                // parity of the next bulk copy to complete
-    const smem_tab_t xft = smem_tab(S.xf);                 // S.lut lies 256 bytes below, S.lut2 256 above: one register
+    // The integer ALU (LOP3, SHF, PRMT, ISETP, VIMNMX: half the issue rate) is the busiest unit of this kernel and the
+    // multiply-add pipe is nearly idle, so additions that ptxas would place on the ALU are written as one_r * x + y:
+    // one_r is 1 in a register ptxas can neither fold nor re-load from the constant bank (full warps: 32 >> 5).
+    const uint32_t one_r = A.one & ((uint32_t)__popc(__activemask()) >> 5);
+    const smem_tab_t xft = smem_tab(S.xf);                 // S.lut lies 256 bytes below: one register
     if (tid == 0 && !smem_tab_ok(xft)) atomicOr(A.err, ERR_ALIGN);
     for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
     if (tid < 16) S.pre[tid] = ZC8;
@@ -919,7 +944,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const bool need_walk = HPC && (int64_t)S.s0 < W0 && hk_real < A.need;
         const bool try_packed = !need_walk && l <= PK_LMAX;
         if (try_packed) {
-            if (compact_packed(S, xft, w, k16, qj) & 0x80u) S.rare = 1u;
+            if (compact_packed(S, w, k16, qj, A.vmask)) S.rare = 1u;
         } else {
             if (S.code_raw) reset_codes(S);                // uniform; every thread read its pieces before the last barrier
             compact_bytes<HPC>(S, xft, w, k16, qj);
@@ -1043,7 +1068,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 }
                 if (v0 == 0) invalid[0] |= lowmask64((uint32_t)dlt);   // the pseudo-owners inside the halo
                 if (packed) {
-                    hash_owners_packed<W31, DENSE>(S, xft, XB + hk + v0 - d, l, A.thr, hs + v0, mask);
+                    hash_owners_packed<W31, DENSE>(S, xft, XB + hk + v0 - d, l, A.thr, hs + v0, mask, one_r);
                 } else {
                     const uint8_t *cb = S.code + XB + hk + v0 - d; // cb[i]: last base of owner i's l-mer; 4-aligned
                     const uint32_t rare = hash_owners_words<W31, DENSE>(S, xft, cb, l, A.thr, hs + v0, mask);

@@ -229,6 +229,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
     return r;
 }
 static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
+static inline unsigned __activemask() { return 0xffffffffu; }     // kernels here run full warps
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
