@@ -129,6 +129,7 @@ struct Smem {
     alignas(256) uint2 gm[32];               // packed compaction: keep nibble -> (gather multiplier, 2 * kept); 16 live entries
     alignas(128) uint2 x2[XFN];
     uint2    x4[256];                        // warm-up: (c0,c1,c2,c3) at c0 + 4*c1 + 16*c2 + 64*c3 advances the state by 4 bases
+    uint2    x4r[256];                       // the same entries rotated by 4 more: two bytes of codes per rotate (packed warm-up)
     uint2    xrm[64];                        // packed warm-up: what the 0..3 oldest codes of its first byte added (see hash_owners_packed)
     alignas(16) uint32_t pk[PKW];            // packed tiles: 2-bit class of every kept base, 16 per word, same index space as code[]
     uint32_t rare;                           // a thread met a rare class while packing: the tile is redone byte-wise
@@ -288,6 +289,16 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 #endif
+}
+template <bool W31> __device__ __forceinline__ uint32_t rol8(uint32_t x)
+{
+    if (W31) return ((x << 8) | (x >> 23)) & 0x7fffffffu;
+    return __funnelshift_l(x, x, 8);
+}
+template <bool W31> __device__ __forceinline__ uint32_t ror8(uint32_t x)
+{
+    if (W31) return (x >> 8) | ((x & 255u) << 23);
+    return __funnelshift_r(x, x, 8);
 }
 template <bool W31> __device__ __forceinline__ uint32_t rol4(uint32_t x)
 {
@@ -476,12 +487,16 @@ __device__ __forceinline__ void hash_owners_packed(const Smem &S, smem_tab_t xft
     {   // warm-up: bytes nb-1 .. 0 counted back from code E-1 (static positions), oldest first
         const int n = l - 1, nb = (n + 3) >> 2, sur = 4 * nb - n;
 #pragma unroll
-        for (int k = 7; k >= 0; --k) {
+        for (int k = 7; k >= 1; k -= 2) {                  // two bytes per rotate: the older one through the pre-rotated table
+            const uint32_t b1 = ((k < 4 ? R[1] : R[0]) >> (8 * (3 - (k & 3)))) & 0xffu;
+            const uint32_t b0 = ((k - 1 < 4 ? R[1] : R[0]) >> (8 * (3 - ((k - 1) & 3)))) & 0xffu;
             if (k < nb) {
-                const uint32_t by = ((k < 4 ? R[1] : R[0]) >> (8 * (3 - (k & 3)))) & 0xffu;
-                const uint2 tt = S.x4[by];
-                fh = rol4<W31>(fh) ^ tt.x;
-                rh = ror4<W31>(rh) ^ tt.y;
+                const uint2 t1 = S.x4r[b1], t0 = S.x4[b0];
+                fh = rol8<W31>(fh) ^ t1.x ^ t0.x;
+                rh = ror8<W31>(rh) ^ t1.y ^ t0.y;
+            } else if (k - 1 < nb) {                       // nb odd: its oldest byte stands alone
+                const uint2 t0 = S.x4[b0];
+                fh = t0.x; rh = t0.y;
             }
         }
         if (sur) {
@@ -742,7 +757,9 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     if (tid < XFN) { S.xf[tid] = A.xf[tid]; S.x2[tid] = A.x2[tid]; }
     for (int i = tid; i < 256; i += NT) {                   // four warm-up bases at once = two steps of the pair table
         const uint2 a = A.x2[4 * (i & 3) + ((i >> 2) & 3)], b = A.x2[4 * ((i >> 4) & 3) + (i >> 6)];
-        S.x4[i] = make_uint2(rol2<W31>(a.x) ^ b.x, ror2<W31>(a.y) ^ b.y);
+        const uint2 e4 = make_uint2(rol2<W31>(a.x) ^ b.x, ror2<W31>(a.y) ^ b.y);
+        S.x4[i] = e4;
+        S.x4r[i] = make_uint2(rol4<W31>(e4.x), ror4<W31>(e4.y));
     }
     if (tid < 16) {                                        // gm: see compact_packed
         const int wd = 2 * __popc((uint32_t)tid);
@@ -881,7 +898,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 #pragma unroll
                 for (int i = 3; i >= 0; --i) {
                     const uint32_t x = w[4 * j + i] ^ __byte_perm(i ? w[4 * j + i - 1] : prevw, w[4 * j + i], 0x6543u);
-                    const uint32_t nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+                    const uint32_t nz = (x | mad_u32(one_r, x & 0x7f7f7f7fu, 0x7f7f7f7fu)) & 0x80808080u;   // the add as an IMAD
                     kk = __funnelshift_l(nz * 0x00204081u, kk, 4);
                 }
                 k16[j] = kk | st16[j];
