@@ -686,8 +686,8 @@ __device__ __forceinline__ void compact_bytes(Smem &S, smem_tab_t xft, const uin
 // S4, packed form, all arithmetic (no look-up per base).  Per word of four raw bases:
 //   class    V = x & 0x06060606: bits 1-2 of an ASCII base are its class in the order A C T G = 0 1 2 3 (the class
 //            numbering of every table; it also is the 2-bit transport format)
-//   validity the low three bits of a base index an 8-entry byte table held in two registers (PRMT with a data-dependent
-//            selector is a 4-way table look-up): the canonical byte of that index, compared with the base itself.  The
+//   validity 2 * class indexes an 8-entry byte table held in two registers (PRMT with a data-dependent selector is a
+//            4-way table look-up): the canonical base of that class, compared with the base itself.  The
 //            differences are OR-ed up and tested once per thread against vmask (0xff per byte in the scalar profile:
 //            exactly A C G T; 0x0f in the nibble profile: the low nibble decides, src/nthash_avx512_32.rs:178-193).
 //            A set bit = some base of a rare class: the tile is redone in byte form.
@@ -696,7 +696,8 @@ __device__ __forceinline__ void compact_bytes(Smem &S, smem_tab_t xft, const uin
 //            32 - 2*kept + 2*rank(j); the other partial products fall off the top or below the field, no two on the
 //            same bits (so no carry).  A funnel shift pushes the field into the accumulator from below, last word
 //            first.
-// Nine ALU instructions and one multiply per word; two shared-memory atomics per piece.
+// Eight ALU instructions and one multiply per word; two shared-memory atomics per piece.  (A 256-entry table fetched
+// once per two words measured slower: 11.62 against 11.54 ms per 10 Gbp.)
 __device__ __forceinline__ uint32_t compact_packed(Smem &S, const uint32_t (&w)[16], const uint32_t (&k16)[4],
                                                    const uint32_t (&qj)[4], uint32_t vmask)
 {
@@ -708,17 +709,17 @@ __device__ __forceinline__ uint32_t compact_packed(Smem &S, const uint32_t (&w)[
 #pragma unroll
         for (int i = 3; i >= 0; --i) {                     // last word first: the first kept base ends up in the low bits
             const uint32_t x = w[4 * j + i];
-            const uint32_t y = x & 0x07070707u;
-            const uint32_t sel = y + (y >> 12);                                    // nibbles: y0 y2 y1 y3
-            uint32_t canon;
+            const uint32_t v = x & 0x06060606u;                                    // 2 * class of the four bases
+            const uint32_t sel = v + (v >> 12);                                    // nibbles: v0 v2 v1 v3
+            uint32_t canon;                                                        // A C T G at indices 0 2 4 6
 #ifdef S2K_EMU
-            canon = __byte_perm(0x43014101u, 0x47000054u, sel);
+            canon = __byte_perm(0x00430041u, 0x00470054u, sel);
 #else
-            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(canon) : "r"(0x43014101u), "r"(0x47000054u), "r"(sel));
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(canon) : "r"(0x00430041u), "r"(0x00470054u), "r"(sel));
 #endif
             bad |= canon ^ __byte_perm(x, 0u, 0x3120u);
             const uint2 e = *reinterpret_cast<const uint2 *>(gm + (((k16[j] << 3) >> (4 * i)) & 0x78u));
-            acc = __funnelshift_l((x & 0x06060606u) * e.x, acc, e.y);
+            acc = __funnelshift_l(v * e.x, acc, e.y);
         }
         const uint32_t p0 = (uint32_t)XB + qj[j], sh = 2u * (p0 & 15u);
         const uint32_t lo = acc << sh, hi = __funnelshift_l(acc, 0u, sh);
