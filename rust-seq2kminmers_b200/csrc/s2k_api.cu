@@ -495,7 +495,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         B.min_loc = ptr<uint64_t>(ctx->d_min_loc);
         B.hpc_loc = want_hpc_off ? ptr<uint64_t>(ctx->d_hpc_off) : nullptr;
         B.tile_pre = ptr<ulonglong2>(ctx->d_tile_pre);
-        B.seq_off = d_seq_off; B.bases = d_bases; B.n_seqs = n_seqs;
+        B.seq_off = d_seq_off; B.bases = d_bases; B.n_seqs = n_seqs; B.n_bases = n_bases;
         B.l = P.l; B.k = P.k; B.quirk = P.quirk; B.hpc = P.hpc;
         B.min_off = ptr<uint64_t>(ctx->d_min_off);
         B.km_off = ptr<uint64_t>(ctx->d_km_off);

@@ -1346,7 +1346,7 @@ struct K2Args {
     const uint64_t *seq_off;
     const uint8_t  *bases;
     const ulonglong2 *tile_pre;          // n_tiles + 1: (minimizers, kept bases) before each tile (k_finalize)
-    uint64_t  n_seqs;
+    uint64_t  n_seqs, n_bases;
     uint32_t  l, k;
     int32_t   quirk, hpc;
     uint64_t *min_off;             // n_seqs + 1, out: global exclusive prefix of per-sequence minimizer counts
@@ -1409,6 +1409,33 @@ __device__ __forceinline__ uint32_t tail_rule_count(const K2Args &A, uint64_t so
     } else {
         uint64_t g = se;
         int found = 0;
+        // Fast form: the last 48 bases as six aligned words fetched at once (the byte-wise walk below is a chain of some
+        // twenty dependent loads, and with short reads one sequence in sixteen comes here), keep bits of the 47 bases
+        // whose predecessor is among them, the 16th set bit from the top.  Fewer than 16 kept bases in that stretch, a
+        // sequence shorter than it or the end of the batch: the walk.
+        const uint64_t p = (se - 41) & ~7ull;
+        if (se >= so + 48 && p + 48 <= A.n_bases && (reinterpret_cast<uintptr_t>(A.bases) & 7u) == 0) {
+            const unsigned long long *wp = reinterpret_cast<const unsigned long long *>(A.bases + p);
+            unsigned long long wv[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) wv[i] = wp[i];
+            unsigned long long km = 0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const unsigned long long x = wv[i] ^ ((wv[i] << 8) | (i ? wv[i - 1] >> 56 : 0ull));
+                const unsigned long long nz = (((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x) & 0x8080808080808080ull;
+                km |= (((nz >> 7) * 0x0102040810204080ull) >> 56) << (8 * i);
+            }
+            km &= ~1ull;                                // the first byte has no predecessor here
+            const uint32_t n_in = (uint32_t)(se - p);   // bytes [p, se) belong to the sequence: 41 .. 48 of them
+            if (n_in < 48) km &= (1ull << n_in) - 1ull;
+            if (__popcll(km) >= 16) {
+#pragma unroll 1
+                for (int i = 0; i < 15; ++i) km &= ~(1ull << (63 - __clzll((long long)km)));
+                g = p + (uint64_t)(63 - __clzll((long long)km));
+                found = 16;
+            }
+        }
         while (found < 16) {                            // M >= 16 guarantees termination above `so`
             --g;
             if (g == so || A.bases[g] != A.bases[g - 1]) ++found;
@@ -1439,8 +1466,17 @@ __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Ar
     S2K_SHARED uint32_t wsum[RT / 32];
     S2K_SHARED unsigned long long s_excl;
     S2K_SHARED uint32_t s_tile;
+    // Sequences the tail rule applies to (one in sixteen with short reads) are listed here and settled one per thread:
+    // inside the per-thread loop some lane of almost every warp would take that path, a chain of dependent loads, and
+    // the whole warp would wait for it once per sequence.
+    S2K_SHARED uint32_t q_n;
+    S2K_SHARED uint16_t q_slot[RT * RPT];                  // thread * RPT + j
+    S2K_SHARED uint32_t q_cnt[RT * RPT];                   // minimizers before the rule
+    S2K_SHARED uint32_t q_res[RT * RPT];                   // by slot: minimizers after it
+    S2K_SHARED unsigned long long q_m0[RT * RPT];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t n_tiles = (A.n_seqs + RT * RPT - 1) / (RT * RPT);
+    if (tid == 0) q_n = 0;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_tile = atomicAdd(A.ticket, 1u);
@@ -1462,17 +1498,38 @@ __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Ar
                 gk[j] = A.hpc_loc ? A.hpc_loc[r] + pre.y : so;
             }
         }
-        uint32_t items[RPT], sum = 0;
+        uint32_t items[RPT], sum = 0, cj[RPT], ruled = 0;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const uint64_t r = r0 + j;
+            cj[j] = r < A.n_seqs ? (uint32_t)(gm[j + 1] - gm[j]) : 0u;
+            if (A.quirk && r < A.n_seqs && cj[j] > 0) {
+                const uint64_t M = gk[j + 1] - gk[j];
+                if (M >= (uint64_t)A.l + 16 && ((M - A.l + 1) & 15) == 0) {
+                    const uint32_t e = atomicAdd(&q_n, 1u);
+                    q_slot[e] = (uint16_t)(tid * RPT + j); q_cnt[e] = cj[j]; q_m0[e] = gm[j];
+                    ruled |= 1u << j;
+                }
+            }
+        }
+        if (A.quirk) {                                     // uniform
+            __syncthreads();
+            const uint32_t qn = q_n;
+            for (uint32_t e = tid; e < qn; e += RT) {
+                const uint64_t r = (uint64_t)t * (RT * RPT) + q_slot[e];
+                q_res[q_slot[e]] = tail_rule_count(A, A.seq_off[r], A.seq_off[r + 1], q_m0[e], q_cnt[e]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                if ((ruled >> j) & 1u) cj[j] = q_res[tid * RPT + j];
+            if (tid == 0) q_n = 0;                         // the next tile's first use lies behind two barriers
+        }
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             items[j] = 0;
             const uint64_t r = r0 + j;
-            uint32_t c = r < A.n_seqs ? (uint32_t)(gm[j + 1] - gm[j]) : 0u;
-            if (A.quirk && r < A.n_seqs && c > 0) {
-                const uint64_t M = gk[j + 1] - gk[j];
-                if (M >= (uint64_t)A.l + 16 && ((M - A.l + 1) & 15) == 0)
-                    c = tail_rule_count(A, A.seq_off[r], A.seq_off[r + 1], gm[j], c);
-            }
+            const uint32_t c = cj[j];
             if (r < A.n_seqs) {
                 A.min_cnt[r] = c;
                 A.min_off[r] = gm[j];
