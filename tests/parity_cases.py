@@ -47,6 +47,24 @@ def cases(B, fixture_seq, scale=1):
     # non-ACGT bytes: N, lower case, IUPAC, junk (scalar table vs nibble table)
     b, so = B.batch([3000, 5000, 100, 20000], alphabet=b"ACGTNacgtnXRY-")
     out.append(("non-ACGT", b, so, all_modes(21, 4, 0.1)))
+    # clean ACGT sequences with ONE other byte each: the packed tiles' validity test (PRMT table look-up against the
+    # base itself) has to turn exactly that tile back to the byte form -- at tile and halo boundaries, as the first and
+    # last base of a word, a piece and a sequence; bytes that are a base in the nibble profile only (lower case, 'Q' =
+    # 0x51 -> A, 'D' = 0x44 -> T, 0x81, 0xc3), bytes that are none in either (0, 'N', 'L' = 0x4c, 0xff, '@', 'E', 'U')
+    specials = [ord("N"), ord("a"), ord("t"), 0x00, 0x81, 0xC3, 0x51, 0x44, 0x4C, 0xFF, 0x40, 0x45, 0x55, 0x57, 0x37, 0x14]
+    places = [0, 1, 3, 4, 15, 16, 63, 64, 15871, 15872, 15873, 16127, 16128, 16129, 16383, 16384, 19999]
+    seqs = []
+    for i, pos in enumerate(places):
+        q = B.seq(20000)
+        q[pos] = specials[i % len(specials)]
+        seqs.append(q)
+    for i, sp in enumerate(specials):
+        q = B.seq(600)
+        q[37 + i] = sp
+        seqs.append(q)
+    seqs.append(B.seq(20000))
+    b, so = B.pack(seqs)
+    out.append(("one-odd-byte", b, so, all_modes(31, 3, 0.05) + [(12, 2, 0.2, HPCSIMD, 0), (12, 2, 0.2, HPC, 0)]))
     # large l (scalar profiles only), incl. halo 512 path
     b, so = B.batch([30000, 700, 255, 256, 257, 100], runp=0.3)
     out.append(("big-l", b, so, [(l, 3, 0.05, m, 0) for m in (REG, HPC) for l in (64, 127, 128, 200, 255)]))
