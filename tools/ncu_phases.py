@@ -17,7 +17,29 @@ hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 I, S, SRC = ix["Instructions Executed"], ix["# Samples"], ix["Source"]
 stall_cols = [(h, i) for h, i in ix.items() if h.startswith("stall_") and "Not Issued" not in h]
-segs, cur = [], {"n": 0, "s": 0, "ops": collections.Counter(), "first": 0, "stalls": collections.Counter(), "lines": []}
+ALU = {"LOP3", "SHF", "PRMT", "ISETP", "VIMNMX", "SEL", "IADD3", "VIADD", "LEA", "R2P", "PLOP3", "VIADDMNMX", "MOV", "CS2R", "S2R", "P2R"}
+LSU = {"LDS", "STS", "LDG", "STG", "ATOMS", "ATOMG", "RED", "LDC", "LDCU", "ATOM", "SYNCS", "UBLKCP", "CCTL"}
+CBU = {"BRA", "BSSY", "BSYNC", "BAR", "EXIT", "WARPSYNC", "NOP", "BREAK", "YIELD"}
+
+
+def pipe(op):                       # issue class of an opcode (ALU and FMA each take a warp instruction every other cycle)
+    if op.startswith("IMAD") or op in ("FFMA", "FMUL", "FADD"):
+        return "fma"
+    if op in ALU:
+        return "alu"
+    if op in LSU:
+        return "lsu"
+    if op in CBU:
+        return "branch"
+    return "other"
+
+
+def new_seg(first):
+    return {"n": 0, "s": 0, "ops": collections.Counter(), "first": first, "stalls": collections.Counter(), "lines": [],
+            "pipe": collections.Counter()}
+
+
+segs, cur = [], new_seg(0)
 tot = ts = 0
 for k, r in enumerate(rows[2:]):
     if len(r) <= I:
@@ -28,7 +50,7 @@ for k, r in enumerate(rows[2:]):
         continue
     toks = r[SRC].split()
     op = toks[1] if toks and toks[0].startswith("@") and len(toks) > 1 else (toks[0] if toks else "?")
-    cur["n"] += e; cur["s"] += s; cur["ops"][op.split(".")[0]] += e
+    cur["n"] += e; cur["s"] += s; cur["ops"][op.split(".")[0]] += e; cur["pipe"][pipe(op.split(".")[0])] += e
     cur["lines"].append((k, e, s, r[SRC].strip()))
     for h, i in stall_cols:
         try:
@@ -38,15 +60,20 @@ for k, r in enumerate(rows[2:]):
     tot += e; ts += s
     if op.startswith("BAR") or op.startswith("EXIT"):
         segs.append(cur)
-        cur = {"n": 0, "s": 0, "ops": collections.Counter(), "first": k + 1, "stalls": collections.Counter(), "lines": []}
+        cur = new_seg(k + 1)
 segs.append(cur)
 print(f"total warp instructions {tot:.4g} = {tot * 32 / bases:.2f} thread-instr/base; stall samples {ts}")
+allp = collections.Counter()
+for g in segs + [cur]:
+    allp.update(g["pipe"])
+print("by issue class (thread-instr/base): " + ", ".join(f"{c} {allp[c] * 32 / bases:.2f}" for c in ("alu", "fma", "lsu", "branch", "other")))
 for j, g in enumerate(segs):
     if g["n"] == 0:
         continue
     ops = ", ".join(f"{o} {c * 32 / bases:.2f}" for o, c in g["ops"].most_common(8))
     st = ", ".join(f"{h[6:]} {c / max(1, ts):.3f}" for h, c in g["stalls"].most_common(4))
-    print(f"seg {j:2d} sass#{g['first']:5d} {g['n'] * 32 / bases:6.2f}/base stall {g['s'] / max(1, ts):5.3f} | {ops} | {st}")
+    pp = " ".join(f"{c} {g['pipe'][c] * 32 / bases:.2f}" for c in ("alu", "fma", "lsu", "branch", "other"))
+    print(f"seg {j:2d} sass#{g['first']:5d} {g['n'] * 32 / bases:6.2f}/base stall {g['s'] / max(1, ts):5.3f} | {pp} | {ops} | {st}")
     if dump:
         for k, e, s, src in g["lines"]:
             if e:
