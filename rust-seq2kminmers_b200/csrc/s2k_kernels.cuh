@@ -119,6 +119,12 @@ struct K1Args {
     uint2     xy[XYN];           // byte offset 8*code(out)+code(in) -> (rol(h[out],l)^h[in], ror(rc[out],1)^rol(rc[in],l-1))
     uint2     xf[XFN];           // the same for ACGT x ACGT at byte offset 4*code(out)+code(in)
     uint2     x2[XFN];           // (c1,c2) at 4*code(c1)+code(c2) -> (rol(h[c1],1)^h[c2], ror(r[c1],1)^r[c2]), r[c]=rol(rc[c],l-1)
+    // H = u64 flavour (src/lib.rs:30-32 `pub type H = u64`, 64-bit ntHash1 seeds, src/nthash_hpc.rs:30-49): the same
+    // (out,in) table with 64-bit entries (x,y = forward low/high, z,w = reverse low/high), the bound, and where the
+    // high halves of the selected hashes go (min_out[i].x holds the low half).  Used by k_minimizers<..., H64 = true>.
+    uint4     xy64[XYN];
+    uint64_t  thr64;
+    uint32_t *min_hi;
 };
 
 struct Smem {
@@ -150,6 +156,7 @@ struct Smem {
     uint32_t ctxpos[XB];                     // walk-back context: distance below W0
     uint16_t qmap[(XB + WIN) / 64 + 2];      // chunk holding kept base 64*m (coarse inverse of qoff)
     uint2    xy[XYN];
+    uint4    xy64[XYN];                      // H = u64 flavour only
     uint16_t hl[HL];
     uint8_t  sel8[256 * 8];                  // sel8[8*b + r] = position of the r-th set bit of byte b (r < popc(b))
     uint32_t wsum[3][NT / 32];               // warp totals: kept-count scan, hit-count scan of pass 0 / pass 1
@@ -376,6 +383,29 @@ __device__ __forceinline__ void hash_owners_bytes(const Smem &S, const uint8_t *
         rh = ror1<W31>(rh) ^ tt.y;
         const uint32_t hv = min(fh, rh);
         if (hv <= thr) { mask[i >> 6] |= 1ull << (i & 63); hs[i] = hv; }
+    }
+}
+// hash_owners_bytes64: the H = u64 flavour (64-bit state per strand, `hash <= bound` on 64 bits).  Low halves of the
+// selected hashes go to hs[i], high halves to hs[WIN + i].  The byte form of the tile is the only one it has.
+__device__ __forceinline__ uint64_t rol1_64(uint64_t x) { return (x << 1) | (x >> 63); }
+__device__ __forceinline__ uint64_t ror1_64(uint64_t x) { return (x >> 1) | (x << 63); }
+__device__ __forceinline__ void hash_owners_bytes64(const Smem &S, const uint8_t *cb, int l, uint64_t thr, uint32_t *hs,
+                                                    unsigned long long (&mask)[MW])
+{
+    uint64_t fh = 0, rh = 0;
+    for (int j = 1 - l; j < 0; ++j) {                  // warm-up: first l-1 bases of owner 0's l-mer
+        const uint4 tt = S.xy64[ZC8 + (cb[j] >> 3)];
+        fh = rol1_64(fh) ^ ((uint64_t)tt.y << 32 | tt.x);
+        rh = ror1_64(rh) ^ ((uint64_t)tt.w << 32 | tt.z);
+    }
+    const uint8_t *co = cb - l;
+#pragma unroll 4
+    for (int i = 0; i < CH; ++i) {
+        const uint4 tt = S.xy64[(i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8) + (cb[i] >> 3)];
+        fh = rol1_64(fh) ^ ((uint64_t)tt.y << 32 | tt.x);
+        rh = ror1_64(rh) ^ ((uint64_t)tt.w << 32 | tt.z);
+        const uint64_t hv = fh < rh ? fh : rh;
+        if (hv <= thr) { mask[i >> 6] |= 1ull << (i & 63); hs[i] = (uint32_t)hv; hs[WIN + i] = (uint32_t)(hv >> 32); }
     }
 }
 // hash_owners_words: the common case, every class among A,C,G,T.  Class bytes are read as words; the four table
@@ -739,14 +769,15 @@ __device__ __forceinline__ void reset_codes(Smem &S)
     if (threadIdx.x == 0) S.code_raw = 0u;
 }
 
-template <bool HPC, bool W31, bool DENSE>
+template <bool HPC, bool W31, bool DENSE, bool H64 = false>
 __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_constant__ K1Args A)
 {
     S2K_DYN_SMEM(smem_raw);
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = (int)A.l, d = (int)A.d;
-    uint32_t *const hs = A.hscr + (size_t)blockIdx.x * WIN;
+    uint32_t *const hs = A.hscr + (size_t)blockIdx.x * (H64 ? 2 * WIN : WIN);
+    if (H64 && tid < XYN) S.xy64[tid] = A.xy64[tid];
 
     for (int i = tid; i < 256; i += NT) S.lut[i] = A.cls_lut[i];
     for (int i = tid; HPC && i < 256 * 8; i += NT) {        // the table-assisted select serves the HPC variants only
@@ -960,7 +991,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // to the byte form after the barrier.
         const uint32_t hk_real = S.hk;
         const bool need_walk = HPC && (int64_t)S.s0 < W0 && hk_real < A.need;
-        const bool try_packed = !need_walk && l <= PK_LMAX;
+        const bool try_packed = !H64 && !need_walk && l <= PK_LMAX;
         if (try_packed) {
             if (compact_packed(S, w, k16, qj, A.vmask)) S.rare = 1u;
         } else {
@@ -1089,11 +1120,15 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                     hash_owners_packed<W31, DENSE>(S, xft, XB + hk + v0 - d, l, A.thr, hs + v0, mask, one_r);
                 } else {
                     const uint8_t *cb = S.code + XB + hk + v0 - d; // cb[i]: last base of owner i's l-mer; 4-aligned
-                    const uint32_t rare = hash_owners_words<W31, DENSE>(S, xft, cb, l, A.thr, hs + v0, mask);
-                    if (rare & RARE4) {                            // a rare class among the bytes touched: redo via xy
+                    if (H64) {
+                        hash_owners_bytes64(S, cb, l, A.thr64, hs + v0, mask);
+                    } else {
+                        const uint32_t rare = hash_owners_words<W31, DENSE>(S, xft, cb, l, A.thr, hs + v0, mask);
+                        if (rare & RARE4) {                        // a rare class among the bytes touched: redo via xy
 #pragma unroll
-                        for (int x = 0; x < MW; ++x) mask[x] = 0ull;
-                        hash_owners_bytes<W31>(S, cb, l, A.thr, hs + v0, mask);
+                            for (int x = 0; x < MW; ++x) mask[x] = 0ull;
+                            hash_owners_bytes<W31>(S, cb, l, A.thr, hs + v0, mask);
+                        }
                     }
                 }
 #pragma unroll
@@ -1193,9 +1228,11 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                 const uint32_t rid = lo - 1;
                 const uint64_t so = cached ? S.soc[lo - lb] : A.seq_off[rid];
                 const uint64_t idx = rec0 + base + j;
-                if (idx < rec_lim)
+                if (idx < rec_lim) {
                     A.min_out[idx] = make_uint4(h, (uint32_t)((uint64_t)g_start - so),
                                                 (uint32_t)((uint64_t)g_own - (uint64_t)d - so), rid);
+                    if (H64) A.min_hi[idx] = hs[WIN + v];
+                }
             }
         }
         PHASE(7);
@@ -1309,6 +1346,8 @@ struct KFArgs {
     uint32_t n_tiles;
     ulonglong2 *tile_pre;        // n_tiles + 1: (minimizers, kept bases) before the tile; entry n_tiles = the totals
     ulonglong2 *tile_src;        // or null: per tile (ordered index of its first record, where its records sit in tmp)
+    const uint32_t *tmp_hi;      // H = u64 flavour: high halves of the hashes, beside tmp / mins (else null)
+    uint32_t *mins_hi;
     int32_t copy;                // 0: leave the records where they are (the window stage reads them through tile_src)
     const uint32_t *err;         // ERR_CAP set: the record store overflowed, the host reruns -- touch nothing
 };
@@ -1333,7 +1372,10 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs
             if (A.tile_src) A.tile_src[t] = make_ulonglong2(bm, src);
         }
         if (A.copy && src + info.x <= A.min_cap)
-            for (uint32_t j = lane; j < info.x; j += 32) A.mins[bm + j] = A.tmp[src + j];
+            for (uint32_t j = lane; j < info.x; j += 32) {
+                A.mins[bm + j] = A.tmp[src + j];
+                if (A.tmp_hi) A.mins_hi[bm + j] = A.tmp_hi[src + j];
+            }
     }
 }
 
@@ -1596,6 +1638,7 @@ struct K3Args {
     uint64_t *hash;
     uint32_t *start, *end;
     uint8_t  *rev;
+    const uint32_t *hash_hi;              // H = u64 flavour (k_windows only): high halves, MixHash<u64> = identity (src/lib.rs:171-177)
 };
 __device__ __forceinline__ uint64_t mix32(uint32_t h)      // MixHash for u32, src/lib.rs:157-169
 {
@@ -1623,7 +1666,7 @@ __global__ void __launch_bounds__(256) k_windows(const __grid_constant__ K3Args 
         uint32_t end = first.z;
         for (uint32_t tt = 0; tt < A.k; ++tt) {
             const uint4 mrec = tt ? A.mins[g + tt] : first;
-            const uint64_t m = mix32(mrec.x);
+            const uint64_t m = A.hash_hi ? ((uint64_t)A.hash_hi[g + tt] << 32 | mrec.x) : mix32(mrec.x);
             f ^= rol64(m, A.k - 1 - tt);
             r ^= rol64(m, tt);
             end = mrec.z;
