@@ -16,7 +16,7 @@ pub enum HashMode { Regular = 0, Hpc = 1, Simd = 2, HpcSimd = 3 }
 /// Which rolling hash: ntHash1-32 (what the crate compiles) or the 31-bit hybrid of `src/nthash2_avx512_32.rs`.
 #[repr(i32)]
 #[derive(Clone, Copy, Debug, PartialEq, Eq)]
-pub enum HashVariant { Nt1_32 = 0, Nt2_31 = 1 }
+pub enum HashVariant { Nt1_32 = 0, Nt2_31 = 1, Nt1_64 = 2 }
 
 /// `KminmerHash` (`src/kminmer.rs:128-135`); equality and order by `hash` only (`src/kminmer.rs:181-203`).
 #[derive(Clone, Copy, Debug)]

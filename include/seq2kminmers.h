@@ -44,7 +44,13 @@ typedef enum s2k_hash_mode {
  * defined for the SIMD modes, whose iterator it would replace. */
 typedef enum s2k_hash_variant {
     S2K_HASH_NT1_32 = 0,
-    S2K_HASH_NT2_31 = 1
+    S2K_HASH_NT2_31 = 1,
+    S2K_HASH_NT1_64 = 2   /* the crate built with `pub type H = u64` (src/lib.rs:30-32): 64-bit ntHash1 seeds
+                             (src/nthash_hpc.rs:30-49), bound = (density * u64::MAX as f64) as u64 (src/lib.rs:91),
+                             `hash <= bound`, MixHash<u64> = identity (src/lib.rs:171-177).  Modes Regular and Hpc only
+                             (the SIMD iterators are 32-bit).  Pinned by the reference's own golden vector for that
+                             build, tests/main.rs:18-39.  result.minimizers[i].hash then holds the LOW half of the
+                             minimizer's hash; s2k_last_minimizer_hash_hi gives the high halves. */
 } s2k_hash_variant;
 
 /* Status codes.  The reference panics (unwrap/assert) where these are returned:
@@ -209,6 +215,11 @@ int s2k_synth_device(s2k_ctx *ctx, uint64_t seed, uint64_t first, uint64_t count
 /* Selection bounds exactly as the reference derives them (src/lib.rs:91, src/nthash_avx512_32.rs:47-48,
  * src/nthash2_avx512_32.rs:52-54). */
 void s2k_bounds(double density, uint32_t *bound_scalar, uint32_t *bound_simd, uint32_t *bound_31);
+/* ... and with H = u64 (src/lib.rs:91): (density * (u64::MAX as f64)) as u64, saturating. */
+uint64_t s2k_bound_u64(double density);
+/* After a DEVICE run with S2K_HASH_NT1_64: device pointer to the high 32 bits of every minimizer's hash, index-aligned
+ * with result.minimizers (valid until the next run on the context); NULL after any other run. */
+int s2k_last_minimizer_hash_hi(const s2k_ctx *ctx, const uint32_t **d_hi);
 
 /* Pinned host memory for callers that want s2k_run's H2D copies to run at full PCIe rate. */
 int  s2k_host_alloc(size_t bytes, void **out);

@@ -20,7 +20,7 @@
 namespace s2k {
 
 enum class HashMode : int { Regular = 0, Hpc = 1, Simd = 2, HpcSimd = 3 };
-enum class HashVariant : int { NT1_32 = 0, NT2_31 = 1 };
+enum class HashVariant : int { NT1_32 = 0, NT2_31 = 1, NT1_64 = 2 };
 
 struct Error : std::runtime_error {
     int status;

@@ -44,9 +44,11 @@ class HashMode(enum.IntEnum):
 
 
 class HashVariant(enum.IntEnum):
-    """NT1_32: src/nthash_avx512_32.rs / src/nthash_hpc.rs; NT2_31: src/nthash2_avx512_32.rs."""
+    """NT1_32: src/nthash_avx512_32.rs / src/nthash_hpc.rs; NT2_31: src/nthash2_avx512_32.rs; NT1_64: the crate built
+    with `pub type H = u64` (src/lib.rs:30-32; modes Regular and Hpc; golden vector tests/main.rs:18-39)."""
     NT1_32 = 0
     NT2_31 = 1
+    NT1_64 = 2
 
 
 class S2KError(RuntimeError):
@@ -88,6 +90,7 @@ ABI_SYMBOLS = (
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
     "s2k_ctx_set_slab_bytes", "s2k_run_fastx", "s2k_last_fastx", "s2k_ctx_set_transport",
     "s2k_last_transport", "s2k_run_packed2", "s2k_pack2", "s2k_count_device", "s2k_count_partition_device", "s2k_count_part",
+    "s2k_bound_u64", "s2k_last_minimizer_hash_hi",
 )
 
 
@@ -114,6 +117,10 @@ class Library:
         L.s2k_run_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(_Params), vp, C.POINTER(_Result)]
         L.s2k_encode_rle.restype = C.c_int
         L.s2k_encode_rle.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(_RleResult)]
+        L.s2k_bound_u64.restype = C.c_uint64
+        L.s2k_bound_u64.argtypes = [C.c_double]
+        L.s2k_last_minimizer_hash_hi.restype = C.c_int
+        L.s2k_last_minimizer_hash_hi.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.s2k_bounds.restype = None
         L.s2k_bounds.argtypes = [C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.s2k_host_alloc.restype = C.c_int

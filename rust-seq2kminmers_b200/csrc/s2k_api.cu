@@ -90,6 +90,8 @@ struct s2k_ctx {
     // device buffers
     Buf d_bases, d_seq_off, d_tile_lb, d_status, d_small, d_mins, d_min_off, d_min_loc, d_tile_pre, d_hpc_off, d_km_off, d_min_cnt;
     Buf d_hash, d_start, d_end, d_rev, d_rle_hpc, d_rle_pos, d_hscr, d_tmp, d_tile_info, d_tile_base, d_tile_src;
+    Buf d_tmp_hi, d_mins_hi;           // H = u64 flavour: high halves of the minimizer hashes
+    bool min_hi_valid = false;
     Buf d_ct_keys, d_ct_cnt, d_ct_first, d_ct_side, d_co_hash, d_co_cnt, d_co_first, h_ct_side;   // s2k_count_device
     // pinned host result buffers
     Buf h_hash, h_start, h_end, h_rev, h_km_off, h_mins, h_min_off, h_min_cnt, h_small, h_rle_hpc, h_rle_pos;
@@ -244,6 +246,9 @@ namespace {
 
 struct Plan {
     bool hpc, simd, w31, quirk;
+    bool h64 = false;            // H = u64 flavour (S2K_HASH_NT1_64): 64-bit ntHash1, `hash <= bound` on 64 bits
+    uint64_t thr64 = 0;
+    uint4 xy64[XYN];
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
     bool dense;      // >= ~0.5 % of the owners selected: bookkeeping per owner instead of a test per group of four
@@ -257,12 +262,15 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
 {
     if (!p) return fail(ctx, S2K_ERR_NULL, "params is null");
     if (p->mode < S2K_MODE_REGULAR || p->mode > S2K_MODE_HPCSIMD) return fail(ctx, S2K_ERR_BAD_PARAM, "unknown hash mode");
-    if (p->variant != S2K_HASH_NT1_32 && p->variant != S2K_HASH_NT2_31) return fail(ctx, S2K_ERR_BAD_PARAM, "unknown hash variant");
+    if (p->variant != S2K_HASH_NT1_32 && p->variant != S2K_HASH_NT2_31 && p->variant != S2K_HASH_NT1_64)
+        return fail(ctx, S2K_ERR_BAD_PARAM, "unknown hash variant");
     if (p->l == 0 || p->k == 0) return fail(ctx, S2K_ERR_BAD_PARAM, "l and k must be >= 1");
     P.hpc = p->mode == S2K_MODE_HPC || p->mode == S2K_MODE_HPCSIMD;
     P.simd = p->mode == S2K_MODE_SIMD || p->mode == S2K_MODE_HPCSIMD;
     P.w31 = p->variant == S2K_HASH_NT2_31;
     if (P.w31 && !P.simd) return fail(ctx, S2K_ERR_BAD_PARAM, "the 31-bit variant replaces the SIMD iterator only (modes Simd/HpcSimd)");
+    P.h64 = p->variant == S2K_HASH_NT1_64;
+    if (P.h64 && P.simd) return fail(ctx, S2K_ERR_BAD_PARAM, "H = u64 exists for the scalar iterators only (modes Regular/Hpc): the SIMD iterators are 32-bit (src/nthash_avx512_32.rs)");
     if (P.simd && p->l > 31) return fail(ctx, S2K_ERR_L_TOO_BIG, "l must be <= 31 in the Simd/HpcSimd modes");
     if (!P.simd && p->l >= 256) return fail(ctx, S2K_ERR_L_TOO_BIG, "l must be < 256 in the Regular/Hpc modes");
     if (p->k > 0x7fffffffu) return fail(ctx, S2K_ERR_BAD_PARAM, "k too large");
@@ -279,6 +287,11 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     P.none = excl == 0;
     P.thr = P.none ? 0u : (uint32_t)(excl - 1);
     P.dense = (double)excl / (P.w31 ? 2147483648.0 : 4294967296.0) >= 0.0027;   // the canonical minimum doubles the rate
+    if (P.h64) {                                     // src/lib.rs:91 with H = u64: ((density as f64) * (u64::MAX as f64)) as u64
+        P.thr64 = s2k_bound_u64(p->density);
+        P.none = false;                              // `hash <= 0` still selects a hash of 0
+        P.dense = (double)P.thr64 / 18446744073709551616.0 >= 0.0027;
+    }
     // base classes: 0..3 = A C T G (bits 1-2 of the ASCII byte: the packed compaction classifies with one AND),
     // 4 = seed 0, 5 = seed 1.  SEED64 is in the order A C G T; the complement of seed s is seed 3 - s.
     const int w = P.w31 ? 31 : 32;
@@ -312,17 +325,33 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
                     make_uint2(rolw(h[o], 1, w) ^ h[i], rorw(rolw(rc[o], P.l - 1, w), 1, w) ^ rolw(rc[i], P.l - 1, w));
             }
         }
+    if (P.h64) {                                     // 64-bit seeds (src/nthash_hpc.rs:30-49), scalar base map: N -> 0, other -> 1
+        uint64_t h6[8] = {0}, r6[8] = {0};
+        for (int b = 0; b < 4; ++b) { h6[b] = SEED64[seed_of[b]]; r6[b] = SEED64[3 - seed_of[b]]; }
+        h6[5] = r6[5] = 1;
+        auto rol = [](uint64_t x, unsigned r) { r &= 63u; return r ? (x << r) | (x >> (64u - r)) : x; };
+        std::memset(P.xy64, 0, sizeof(P.xy64));
+        for (int o = 0; o < 6; ++o)
+            for (int i = 0; i < 6; ++i) {
+                const uint64_t f = rol(h6[o], P.l) ^ h6[i], r = rol(r6[o], 63) ^ rol(r6[i], P.l - 1);
+                P.xy64[(8 * code_of[o] + code_of[i]) / 8] = make_uint4((uint32_t)f, (uint32_t)(f >> 32), (uint32_t)r, (uint32_t)(r >> 32));
+            }
+    }
     return S2K_OK;
 }
 
 template <typename T> T *ptr(Buf &b) { return reinterpret_cast<T *>(b.p); }
 
 typedef void (*MinimizerKernel)(const K1Args);
-MinimizerKernel minimizer_kernel(bool hpc, bool w31, bool dense)
+MinimizerKernel minimizer_kernel(bool hpc, bool w31, bool dense, bool h64 = false)
 {
     static const MinimizerKernel k[8] = {
         k_minimizers<false, false, false>, k_minimizers<true, false, false>, k_minimizers<false, true, false>, k_minimizers<true, true, false>,
         k_minimizers<false, false, true>,  k_minimizers<true, false, true>,  k_minimizers<false, true, true>,  k_minimizers<true, true, true>};
+    static const MinimizerKernel k64[4] = {
+        k_minimizers<false, false, false, true>, k_minimizers<true, false, false, true>,
+        k_minimizers<false, false, true, true>,  k_minimizers<true, false, true, true>};
+    if (h64) return k64[(hpc ? 1 : 0) | (dense ? 2 : 0)];
     return k[(hpc ? 1 : 0) | (w31 ? 2 : 0) | (dense ? 4 : 0)];
 }
 
@@ -332,6 +361,7 @@ int set_attrs(s2k_ctx *ctx)
     if (ctx->attr_set) return S2K_OK;
     const int smem = (int)sizeof(Smem);
     for (int v = 0; v < 8; ++v) CU(cudaFuncSetAttribute(minimizer_kernel(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int v = 0; v < 4; ++v) CU(cudaFuncSetAttribute(minimizer_kernel(v & 1, false, v & 2, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ctx->attr_set = true;
     return S2K_OK;
 }
@@ -354,7 +384,8 @@ void timing_prepare(s2k_ctx *ctx)
 int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs, uint64_t n_bases,
                const Plan &P, cudaStream_t st, s2k_result *out, bool in_place_ok = false)
 {
-    const bool in_place = in_place_ok && (ctx->flags & S2K_NO_MINIMIZER_STREAM) && P.k <= (uint32_t)KW_MAX;
+    const bool in_place = in_place_ok && (ctx->flags & S2K_NO_MINIMIZER_STREAM) && P.k <= (uint32_t)KW_MAX && !P.h64;
+    ctx->min_hi_valid = false;
     int rc;
     if ((rc = set_attrs(ctx)) != S2K_OK) return rc;
     timing_prepare(ctx);
@@ -390,7 +421,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     // capacity of the minimizer stream: expected 2*density*(kept bases), with head room; grown and rerun on overflow
     uint64_t cap;
     {
-        const double frac = std::min(1.0, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+        const double frac = P.h64 ? std::min(1.0, ((double)P.thr64 + 1.0) / 18446744073709551616.0)
+                                  : std::min(1.0, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
         double rate = std::min(1.0, 2.0 * frac) * 1.15 + 0.0005;
         rate = std::max(rate, ctx->rate_hint * 1.05);
         cap = std::min<uint64_t>(n_bases, (uint64_t)((double)n_bases * rate) + 65536);
@@ -407,8 +439,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     if (n_tiles64 >= 0xfffffff0ull) return fail(ctx, S2K_ERR_BAD_PARAM, "batch too large");
     const uint32_t n_tiles = (uint32_t)n_tiles64;
     const int max_grid = ctx->sm_count * S2K_MINB;
-    const size_t hscr_words = (size_t)max_grid * WIN, smem = sizeof(Smem);
-    void (*kfn)(const K1Args) = minimizer_kernel(P.hpc, P.w31, P.dense);
+    const size_t hscr_words = (size_t)max_grid * WIN * (P.h64 ? 2 : 1), smem = sizeof(Smem);
+    void (*kfn)(const K1Args) = minimizer_kernel(P.hpc, P.w31, P.dense, P.h64);
     const uint32_t n_chunks = (n_tiles + ST - 1) / ST;
     const uint64_t rtiles = (n_seqs + RT * RPT - 1) / (RT * RPT);
     if ((rc = ensure(ctx, ctx->d_tile_lb, ((uint64_t)n_tiles + 1) * 4, false))) return rc;
@@ -432,6 +464,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         const uint64_t item_cap = std::max<uint64_t>(cap, 1);
         if ((rc = ensure(ctx, ctx->d_tmp, tmp_cap * sizeof(uint4), false))) return rc;
         if ((rc = ensure(ctx, ctx->d_mins, (in_place ? 1 : item_cap) * sizeof(uint4), false))) return rc;
+        if (P.h64 && (rc = ensure(ctx, ctx->d_tmp_hi, tmp_cap * 4, false))) return rc;
+        if (P.h64 && (rc = ensure(ctx, ctx->d_mins_hi, item_cap * 4, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_hash, item_cap * 8, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_start, item_cap * 4, false))) return rc;
         if ((rc = ensure(ctx, ctx->d_end, item_cap * 4, false))) return rc;
@@ -452,6 +486,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
         A.tile = (uint32_t)tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
         A.vmask = P.simd ? 0x0f0f0f0fu : 0xffffffffu; A.one = 1u;
+        A.thr64 = P.thr64; A.min_hi = P.h64 ? ptr<uint32_t>(ctx->d_tmp_hi) : nullptr;
+        if (P.h64) std::memcpy(A.xy64, P.xy64, sizeof(P.xy64)); else std::memset(A.xy64, 0, sizeof(A.xy64));
         std::memcpy(A.cls_lut, P.lut, 256);
         std::memcpy(A.xy, P.xy, sizeof(P.xy));
         std::memcpy(A.xf, P.xf, sizeof(P.xf));
@@ -481,6 +517,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         F.min_cap = tmp_cap; F.n_tiles = n_tiles;
         F.tile_pre = ptr<ulonglong2>(ctx->d_tile_pre);
         F.tile_src = in_place ? ptr<ulonglong2>(ctx->d_tile_src) : nullptr; F.copy = in_place ? 0 : 1;
+        F.tmp_hi = P.h64 ? ptr<uint32_t>(ctx->d_tmp_hi) : nullptr; F.mins_hi = P.h64 ? ptr<uint32_t>(ctx->d_mins_hi) : nullptr;
         F.err = A.err;
         const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 8) / 8, (uint64_t)ctx->sm_count * 8);
         S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
@@ -511,6 +548,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         C.mins = B.mins; C.min_off = B.min_off; C.km_off = B.km_off; C.n_min_p = A.cursor; C.err = A.err; C.k = P.k;
         C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);
         C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
+        C.hash_hi = P.h64 ? ptr<uint32_t>(ctx->d_mins_hi) : nullptr;
         if (in_place) {
             K3TArgs D;
             D.W = C; D.tile_info = ptr<uint4>(ctx->d_tile_info); D.tile_src = B.tile_src; D.n_tiles = n_tiles;
@@ -523,7 +561,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
             }
         } else {
             const int g3 = (int)std::min<uint64_t>((item_cap + 255) / 256, (uint64_t)ctx->sm_count * 16);
-            switch (P.k <= (uint32_t)KW_MAX ? (int)P.k : 0) {
+            switch (P.k <= (uint32_t)KW_MAX && !P.h64 ? (int)P.k : 0) {
 #define S2K_WINDOWS_CASE(K) case K: S2K_LAUNCH(k_windows_w<K>, g3, 256, 0, st, false, C); break;
                 S2K_WINDOWS_CASE(1) S2K_WINDOWS_CASE(2) S2K_WINDOWS_CASE(3) S2K_WINDOWS_CASE(4) S2K_WINDOWS_CASE(5) S2K_WINDOWS_CASE(6)
                 S2K_WINDOWS_CASE(7) S2K_WINDOWS_CASE(8) S2K_WINDOWS_CASE(9) S2K_WINDOWS_CASE(10) S2K_WINDOWS_CASE(11) S2K_WINDOWS_CASE(12)
@@ -555,6 +593,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         float f = 0; cudaEventElapsedTime(&f, T.wv[0], T.wv[1]);
         T.min_ms = ms; T.win_ms = f; T.min_launches = (uint32_t)T.n;
     }
+    ctx->min_hi_valid = P.h64;
     out->n_minimizers = n_min;
     out->n_items = hsmall[4];
     out->hash = ptr<uint64_t>(ctx->d_hash);
@@ -604,6 +643,19 @@ const char *s2k_strerror(int status)
 
 const char *s2k_last_error(const s2k_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+uint64_t s2k_bound_u64(double density)
+{
+    const double v = density * 18446744073709551615.0;       // u64::MAX as f64 == 2^64
+    if (!(v > 0.0)) return 0ull;
+    if (v >= 18446744073709551616.0) return ~0ull;           // Rust `as` saturates
+    return (uint64_t)v;
+}
+int s2k_last_minimizer_hash_hi(const s2k_ctx *ctx, const uint32_t **d_hi)
+{
+    if (!ctx || !d_hi) return S2K_ERR_NULL;
+    *d_hi = ctx->min_hi_valid ? reinterpret_cast<const uint32_t *>(ctx->d_mins_hi.p) : nullptr;
+    return S2K_OK;
+}
 void s2k_bounds(double density, uint32_t *b_scalar, uint32_t *b_simd, uint32_t *b_31)
 {
     const uint32_t bs = bound_scalar(density), bv = bound_simd(bs);
@@ -639,7 +691,7 @@ void s2k_ctx_destroy(s2k_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
     Buf *all[] = {&ctx->d_bases, &ctx->d_seq_off, &ctx->d_tile_lb, &ctx->d_status, &ctx->d_small, &ctx->d_mins,
                   &ctx->d_min_off, &ctx->d_min_loc, &ctx->d_tile_pre, &ctx->d_hpc_off, &ctx->d_km_off, &ctx->d_min_cnt, &ctx->d_hash, &ctx->d_start,
-                  &ctx->d_end, &ctx->d_rev, &ctx->d_ct_keys, &ctx->d_ct_cnt, &ctx->d_ct_first, &ctx->d_ct_side, &ctx->d_co_hash, &ctx->d_co_cnt, &ctx->d_co_first, &ctx->h_ct_side, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->d_tile_src, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
+                  &ctx->d_end, &ctx->d_rev, &ctx->d_ct_keys, &ctx->d_ct_cnt, &ctx->d_ct_first, &ctx->d_ct_side, &ctx->d_co_hash, &ctx->d_co_cnt, &ctx->d_co_first, &ctx->h_ct_side, &ctx->d_rle_hpc, &ctx->d_rle_pos, &ctx->d_hscr, &ctx->d_tmp, &ctx->d_tmp_hi, &ctx->d_mins_hi, &ctx->d_tile_info, &ctx->d_tile_base, &ctx->d_tile_src, &ctx->h_hash, &ctx->h_start, &ctx->h_end,
                   &ctx->h_rev, &ctx->h_km_off, &ctx->h_mins, &ctx->h_min_off, &ctx->h_min_cnt, &ctx->h_small,
                   &ctx->h_rle_hpc, &ctx->h_rle_pos, &ctx->d_in[0], &ctx->d_in[1], &ctx->d_in[2], &ctx->d_in_off[0], &ctx->d_in_off[1], &ctx->d_in_off[2],
                   &ctx->h_off_stage[0], &ctx->h_off_stage[1], &ctx->h_off_stage[2], &ctx->d_piece, &ctx->h_piece, &ctx->d_stage, &ctx->h_fx_bases, &ctx->h_fx_off, &ctx->h_ascii[0], &ctx->h_ascii[1], &ctx->h_ascii[2], &ctx->d_pack[0], &ctx->d_pack[1], &ctx->d_pack[2],

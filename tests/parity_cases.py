@@ -1,6 +1,7 @@
 """Parity cases shared by the emulation tier (CPU, tests/emu) and the GPU tier (C ABI on a B200).
 Each case: (label, bases, seq_off, [(l, k, density, mode, variant), ...])."""
 import numpy as np
+import pytest
 
 REG, HPC, SIMD, HPCSIMD = 0, 1, 2, 3
 
@@ -146,3 +147,37 @@ def empty_tile_cases(B, n_poly=400000, l=31):
     if head[n] == ord("A"):                                # n + 1 would not add a kept base
         seqs[2] = np.concatenate([head[:n + 2], poly])
     return B.pack(seqs)
+
+
+def check_h64_flavour(S, O, ctx, B, fixture_seq, scale=1):
+    """S2K_HASH_NT1_64 (the crate built with `pub type H = u64`, src/lib.rs:30-32): the reference's own golden vector
+    for that build (KAT-2, tests/main.rs:18-39) through the ABI, then items against the oracle's closed form (64-bit
+    seeds src/nthash_hpc.rs:30-49, `hash <= (density * u64::MAX as f64) as u64`, identity mix src/lib.rs:171-177) in the
+    modes it exists for, on batches with empty and short reads, homopolymers, non-ACGT bytes and l beyond 32."""
+    from test_oracle_kats import KAT2
+    V = S.HashVariant.NT1_64
+    it = S.KminmersIterator(fixture_seq, 10, 5, 0.0001, S.HashMode.Regular, variant=V, ctx=ctx)
+    assert [km.get_hash() for km in it] == KAT2
+    lens = [0, 5, 11, 12, 40, 300, 0, 2500, 16000 * scale, 33, 64, 65]
+    b1, so1 = B.batch(lens, runp=0.3)
+    b2, so2 = B.batch([4000, 100, 9000], alphabet=b"ACGTNacgtXRY", runp=0.2)
+    for bases, so in ((b1, so1), (b2, so2)):
+        for mode, l, k, d in ((REG, 10, 5, 0.01), (HPC, 10, 3, 0.02), (REG, 31, 2, 0.05), (HPC, 31, 5, 0.05),
+                              (HPC, 64, 2, 0.1), (REG, 100, 1, 0.3), (HPC, 11, 4, 1.0), (REG, 17, 3, 0.0)):
+            got = ctx.run(bases, so, l, k, d, S.HashMode(mode), V)
+            bound = min(int(d * float(2 ** 64 - 1)), 2 ** 64 - 1)
+            for r in range(len(so) - 1):
+                seq = bases[int(so[r]):int(so[r + 1])]
+                hpc = mode == HPC
+                st, en, h = O.closed_minimizers(seq, l, hpc, False, 64, bound, False, 1 if hpc else 0, 1 if hpc else 0)
+                a, e = int(got.km_off[r]), int(got.km_off[r + 1])
+                if len(h) < k:
+                    assert e == a, (mode, l, k, d, r)
+                    continue
+                wh, wr = O.closed_windows(h, k, mix_u32=False)
+                assert e - a == len(wh), (mode, l, k, d, r, e - a, len(wh))
+                assert np.array_equal(got.hash[a:e], wh) and np.array_equal(got.rev[a:e], wr), (mode, l, k, d, r)
+                assert np.array_equal(got.start[a:e], st[:len(wh)].astype(np.uint32)), (mode, l, k, d, r)
+                assert np.array_equal(got.end[a:e], en[k - 1:].astype(np.uint32)), (mode, l, k, d, r)
+    with pytest.raises(S.S2KError):                    # the SIMD iterators are 32-bit
+        ctx.run(b1, so1, 10, 3, 0.01, S.HashMode.HpcSimd, V)

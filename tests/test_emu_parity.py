@@ -231,3 +231,9 @@ def test_window_stage_in_place_emulated(S, O, emu_ctx, batches, fixture_seq):
     for (l, k, d, mode) in [(31, 5, 0.01, 3), (31, 12, 0.02, 1)]:
         got = run_device_in_place(S, emu_ctx, bases, so, l, k, d, mode, 0, to_device, to_host)
         assert_batch_matches_oracle(O, got, bases, so, l, k, d, mode, 0, check_minimizers=False)
+
+
+def test_h64_flavour_emulated(S, O, emu_ctx, batches, fixture_seq):
+    """H = u64: KAT-2 of the reference (tests/main.rs:18-39) through the kernels, closed-form parity."""
+    from parity_cases import check_h64_flavour
+    check_h64_flavour(S, O, emu_ctx, batches, fixture_seq, scale=1)

@@ -337,3 +337,10 @@ def test_window_stage_in_place(S, O, gpu_ctx, batches, fixture_seq):
     assert outs[0][0] == outs[1][0] > 0
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_h64_flavour(S, O, gpu_ctx, batches, fixture_seq):
+    """H = u64: KAT-2 of the reference (tests/main.rs:18-39) through the kernels, closed-form parity."""
+    from parity_cases import check_h64_flavour
+    check_h64_flavour(S, O, gpu_ctx, batches, fixture_seq, scale=4)
