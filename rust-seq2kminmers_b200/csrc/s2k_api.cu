@@ -455,10 +455,12 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     bool regions = true;                               // per-CTA append regions first; one global allocator on the rerun
     for (int attempt = 0;; ++attempt) {
         if (attempt == 4) return fail(ctx, S2K_ERR_INTERNAL, "minimizer kernel did not converge");
-        // Per-CTA append regions get 1/8 + 1024 records of slack on top of an even share: tiles are handed out
-        // dynamically, so the CTAs' totals differ by a few tiles' worth.
+        // Per-CTA append regions get 3/4 + 1024 records of slack on top of an even share.  Tiles are handed out
+        // dynamically, but the CTAs of one SM do not progress at the same pace when the ALU pipe is saturated (the warp
+        // scheduler prefers the higher warp slots): measured on config-2 shaped batches, the busiest CTA appends more
+        // than 1.33 x the average (HPC off, d = 0.01: an 1/8 slack overflowed on every run and the batch ran twice).
         const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
-        const uint64_t slack = (ctx->flags & S2K_DEBUG_TINY_CAP) ? 1 : cap / (8ull * (uint64_t)grid) + 1024;
+        const uint64_t slack = (ctx->flags & S2K_DEBUG_TINY_CAP) ? 1 : 3ull * cap / (4ull * (uint64_t)grid) + 1024;
         const uint64_t region_cap = regions ? cap / (uint64_t)grid + slack : 0;
         const uint64_t tmp_cap = regions ? region_cap * (uint64_t)grid : cap;
         const uint64_t item_cap = std::max<uint64_t>(cap, 1);
@@ -581,6 +583,9 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         if (errw & ERR_ALIGN) return fail(ctx, S2K_ERR_INTERNAL, "shared-memory tables are not 256-byte aligned");
         if (errw & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "scan look-back timed out");
         if (!(errw & ERR_CAP) && n_min <= cap) break;
+        if (getenv("S2K_TRACE_RERUN"))
+            fprintf(stderr, "[s2k] rerun: err %u, minimizers %llu, cap %llu, region_cap %llu x %d CTAs, tiles %u\n", errw,
+                    (unsigned long long)n_min, (unsigned long long)cap, (unsigned long long)region_cap, grid, n_tiles);
         cap = std::max(cap, n_min);                    // exact size known now: rerun once, with one global allocator
         regions = false;
         T.n = 0;
