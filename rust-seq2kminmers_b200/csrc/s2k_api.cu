@@ -543,9 +543,15 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         B.ticket = reinterpret_cast<uint32_t *>(small + 6);
         B.err = A.err;
         if (T.enabled) cudaEventRecord(T.wv[0], st);
-        const int grid2 = (int)std::min<uint64_t>(rtiles, (uint64_t)ctx->sm_count * 8);
+        const int grid2 = (int)std::min<uint64_t>(rtiles + 1, (uint64_t)ctx->sm_count * 8);
         S2K_LAUNCH(k_read_counts, grid2, RT, 0, st, false, B);
+        K2SArgs Sc;
+        Sc.min_cnt = B.min_cnt; Sc.km_off = B.km_off; Sc.n_seqs = n_seqs; Sc.k = P.k;
+        Sc.status = B.status; Sc.ticket = B.ticket; Sc.err = A.err;
+        const uint64_t stiles = (n_seqs + RT * SPT - 1) / (RT * SPT);
+        S2K_LAUNCH(k_item_scan, (int)std::min<uint64_t>(std::max<uint64_t>(stiles, 1), (uint64_t)ctx->sm_count * 8), RT, 0, st, false, Sc);
         CU(cudaGetLastError());
+        ctx->launches += 1;
         K3Args C;
         C.mins = B.mins; C.min_off = B.min_off; C.km_off = B.km_off; C.n_min_p = A.cursor; C.err = A.err; C.k = P.k;
         C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);

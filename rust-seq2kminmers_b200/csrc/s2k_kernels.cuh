@@ -1502,36 +1502,31 @@ __device__ __forceinline__ uint32_t tail_rule_count(const K2Args &A, uint64_t so
 // Per sequence: the tile-local prefixes of k_minimizers made global (the tile of a sequence = the tile of its first
 // base), minimizers that feed the window stage, item counts, and their exclusive scan (decoupled look-back over tiles
 // of RT * RPT sequences).  One pass over the per-sequence arrays: 16-24 bytes read, 20 written per sequence.
+// k_read_counts: per sequence, the global minimizer prefix (min_off) and the number of minimizers that reach the window
+// stage (min_cnt: the AVX-512 tail rule applied).  A warp takes 32 * RPT consecutive sequences, lane L the sequences
+// base + 32 j + L (coalesced loads; the next sequence's prefixes arrive by shuffle); no block barrier anywhere.  The
+// sequences the rule applies to (one in sixteen with short reads) are listed per warp in shared memory and settled one
+// per lane: inside the per-sequence loop some lane of almost every warp would take that chain of dependent loads and the
+// whole warp would wait for it once per sequence.  The exclusive scan of the item counts is k_item_scan's.
 __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Args A)
 {
     if (*A.err & ERR_CAP) return;                          // the record store overflowed: the host reruns
-    S2K_SHARED uint32_t wsum[RT / 32];
-    S2K_SHARED unsigned long long s_excl;
-    S2K_SHARED uint32_t s_tile;
-    // Sequences the tail rule applies to (one in sixteen with short reads) are listed here and settled one per thread:
-    // inside the per-thread loop some lane of almost every warp would take that path, a chain of dependent loads, and
-    // the whole warp would wait for it once per sequence.
-    S2K_SHARED uint32_t q_n;
-    S2K_SHARED uint16_t q_slot[RT * RPT];                  // thread * RPT + j
-    S2K_SHARED uint32_t q_cnt[RT * RPT];                   // minimizers before the rule
-    S2K_SHARED uint32_t q_res[RT * RPT];                   // by slot: minimizers after it
-    S2K_SHARED unsigned long long q_m0[RT * RPT];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t n_tiles = (A.n_seqs + RT * RPT - 1) / (RT * RPT);
-    if (tid == 0) q_n = 0;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(A.ticket, 1u);
-        __syncthreads();
-        const uint32_t t = s_tile;
-        if (t >= n_tiles) break;
-        const uint64_t r0 = (uint64_t)t * (RT * RPT) + (uint64_t)tid * RPT;
-        uint64_t gm[RPT + 1], gk[RPT + 1];                 // global prefixes of sequences r0 .. r0 + RPT
+    constexpr int WT = 32 * RPT;                           // sequences per warp pass
+    S2K_SHARED uint16_t q_slot[RT / 32][WT];               // 32 j + lane of a listed sequence
+    S2K_SHARED uint32_t q_cnt[RT / 32][WT];                // its minimizers before the rule
+    S2K_SHARED uint32_t q_res[RT / 32][WT];                // by slot: minimizers after it
+    S2K_SHARED unsigned long long q_m0[RT / 32][WT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_pass = A.n_seqs / WT + 1;             // the last pass also writes min_off[n_seqs]
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t ps = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ps < n_pass; ps += n_warps) {
+        const uint64_t base = ps * WT;
+        uint64_t gm[RPT + 1], gk[RPT + 1];                 // global prefixes of sequences base + 32 j + lane (j = RPT: lane 0 only)
 #pragma unroll
         for (int j = 0; j <= RPT; ++j) {
             gm[j] = 0; gk[j] = 0;
-            const uint64_t r = r0 + j;
-            if (r <= A.n_seqs) {
+            const uint64_t r = base + 32 * j + lane;
+            if (r <= A.n_seqs && (j < RPT || lane == 0)) {
                 const uint64_t so = A.seq_off[r];
                 uint32_t ts = tile_of_pos(A, so);
                 if (ts >= A.n_tiles) ts = A.n_tiles - 1;
@@ -1540,54 +1535,94 @@ __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Ar
                 gk[j] = A.hpc_loc ? A.hpc_loc[r] + pre.y : so;
             }
         }
-        uint32_t items[RPT], sum = 0, cj[RPT], ruled = 0;
+        uint32_t cj[RPT], ruled = 0, n_list = 0;
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
-            const uint64_t r = r0 + j;
-            cj[j] = r < A.n_seqs ? (uint32_t)(gm[j + 1] - gm[j]) : 0u;
+            const uint64_t r = base + 32 * j + lane;
+            // prefixes of sequence r + 1: the lane above, or lane 0 of the next row
+            const uint64_t gm_up = __shfl_down_sync(0xffffffffu, gm[j], 1), gk_up = __shfl_down_sync(0xffffffffu, gk[j], 1);
+            const uint64_t gm_row = __shfl_sync(0xffffffffu, gm[j + 1], 0), gk_row = __shfl_sync(0xffffffffu, gk[j + 1], 0);
+            const uint64_t gm1 = lane == 31 ? gm_row : gm_up, gk1 = lane == 31 ? gk_row : gk_up;
+            cj[j] = r < A.n_seqs ? (uint32_t)(gm1 - gm[j]) : 0u;
+            bool need = false;
             if (A.quirk && r < A.n_seqs && cj[j] > 0) {
-                const uint64_t M = gk[j + 1] - gk[j];
-                if (M >= (uint64_t)A.l + 16 && ((M - A.l + 1) & 15) == 0) {
-                    const uint32_t e = atomicAdd(&q_n, 1u);
-                    q_slot[e] = (uint16_t)(tid * RPT + j); q_cnt[e] = cj[j]; q_m0[e] = gm[j];
-                    ruled |= 1u << j;
-                }
+                const uint64_t M = gk1 - gk[j];
+                need = M >= (uint64_t)A.l + 16 && ((M - A.l + 1) & 15) == 0;
             }
+            const uint32_t m = __ballot_sync(0xffffffffu, need);
+            if (need) {
+                const uint32_t e = n_list + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                q_slot[warp][e] = (uint16_t)(32 * j + lane); q_cnt[warp][e] = cj[j]; q_m0[warp][e] = gm[j];
+                ruled |= 1u << j;
+            }
+            n_list += (uint32_t)__popc(m);
         }
-        if (A.quirk) {                                     // uniform
-            __syncthreads();
-            const uint32_t qn = q_n;
-            for (uint32_t e = tid; e < qn; e += RT) {
-                const uint64_t r = (uint64_t)t * (RT * RPT) + q_slot[e];
-                q_res[q_slot[e]] = tail_rule_count(A, A.seq_off[r], A.seq_off[r + 1], q_m0[e], q_cnt[e]);
+        if (n_list) {                                      // warp-uniform
+            __syncwarp();
+            for (uint32_t e = lane; e < n_list; e += 32) {
+                const uint32_t sl = q_slot[warp][e];
+                const uint64_t r = base + sl;
+                q_res[warp][sl] = tail_rule_count(A, A.seq_off[r], A.seq_off[r + 1], q_m0[warp][e], q_cnt[warp][e]);
             }
-            __syncthreads();
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < RPT; ++j)
-                if ((ruled >> j) & 1u) cj[j] = q_res[tid * RPT + j];
-            if (tid == 0) q_n = 0;                         // the next tile's first use lies behind two barriers
+                if ((ruled >> j) & 1u) cj[j] = q_res[warp][32 * j + lane];
+            __syncwarp();                                  // the lists are reused by the next pass
         }
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
-            items[j] = 0;
-            const uint64_t r = r0 + j;
-            const uint32_t c = cj[j];
-            if (r < A.n_seqs) {
-                A.min_cnt[r] = c;
-                A.min_off[r] = gm[j];
-                items[j] = c >= A.k ? c - A.k + 1 : 0;
-            } else if (r == A.n_seqs) {
-                A.min_off[r] = gm[j];
-            }
-            sum += items[j];
+            const uint64_t r = base + 32 * j + lane;
+            if (r < A.n_seqs) { A.min_cnt[r] = cj[j]; A.min_off[r] = gm[j]; }
+            else if (r == A.n_seqs) A.min_off[r] = gm[j];
         }
-        // block scan
+    }
+}
+
+// k_item_scan: items per sequence = max(0, min_cnt - k + 1) (src/lib.rs:231-261: a window needs k minimizers), exclusive
+// scan -> km_off[0 .. n_seqs].  One pass, decoupled look-back over tiles of RT * SPT sequences.
+constexpr int SPT = 8;             // sequences per thread of the scan
+struct K2SArgs {
+    const uint32_t *min_cnt;
+    uint64_t *km_off;
+    uint64_t  n_seqs;
+    uint32_t  k;
+    uint64_t *status;              // per tile, zeroed
+    uint32_t *ticket;
+    uint32_t *err;
+};
+__global__ void __launch_bounds__(RT) k_item_scan(const __grid_constant__ K2SArgs A)
+{
+    if (*A.err & ERR_CAP) return;
+    S2K_SHARED uint32_t wsum[RT / 32];
+    S2K_SHARED unsigned long long s_excl;
+    S2K_SHARED uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t n_tiles = (A.n_seqs + RT * SPT - 1) / (RT * SPT);
+    if (n_tiles == 0) { if (blockIdx.x == 0 && tid == 0) A.km_off[0] = 0; return; }
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        const uint32_t t = s_tile;
+        if (t >= n_tiles) break;
+        const uint64_t r0 = (uint64_t)t * (RT * SPT) + (uint64_t)tid * SPT;
+        uint32_t items[SPT], sum = 0;
+        if (r0 + SPT <= A.n_seqs) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(A.min_cnt + r0), b = *reinterpret_cast<const uint4 *>(A.min_cnt + r0 + 4);
+            items[0] = a.x; items[1] = a.y; items[2] = a.z; items[3] = a.w; items[4] = b.x; items[5] = b.y; items[6] = b.z; items[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < SPT; ++j) items[j] = r0 + j < A.n_seqs ? A.min_cnt[r0 + j] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) { items[j] = items[j] >= A.k ? items[j] - A.k + 1 : 0u; sum += items[j]; }
         uint32_t incl = warp_incl_scan(sum, lane);
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
         uint32_t pre = 0, tot = 0;
 #pragma unroll
-        for (int i = 0; i < RT / 32; ++i) { const uint32_t s = wsum[i]; if (i < warp) pre += s; tot += s; }
+        for (int i = 0; i < RT / 32; ++i) { const uint32_t sw = wsum[i]; if (i < warp) pre += sw; tot += sw; }
         const uint32_t excl_local = pre + incl - sum;
         if (warp == 0) {
             uint64_t excl = 0;
@@ -1596,17 +1631,17 @@ __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Ar
                 int64_t j = (int64_t)t - 1;
                 for (;;) {
                     const int64_t idx = j - lane;
-                    uint64_t s = FLAG_INCL;
+                    uint64_t sv = FLAG_INCL;
                     if (idx >= 0) {
                         uint32_t spins = 0;
-                        while (((s = ld_relaxed(&A.status[idx])) >> 62) == 0) {
-                            if (++spins > SPIN_LIMIT) { atomicOr(A.err, ERR_SPIN); s = FLAG_INCL; break; }
+                        while (((sv = ld_relaxed(&A.status[idx])) >> 62) == 0) {
+                            if (++spins > SPIN_LIMIT) { atomicOr(A.err, ERR_SPIN); sv = FLAG_INCL; break; }
                             __nanosleep(40);
                         }
                     }
-                    const uint32_t im = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+                    const uint32_t im = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
                     const int first = im ? (__ffs(im) - 1) : 32;
-                    excl += warp_sum64(lane <= first ? (s & VALMASK) : 0ull);
+                    excl += warp_sum64(lane <= first ? (sv & VALMASK) : 0ull);
                     if (im) break;
                     j -= 32;
                 }
@@ -1620,7 +1655,7 @@ __global__ void __launch_bounds__(RT) k_read_counts(const __grid_constant__ K2Ar
         __syncthreads();
         uint64_t o = s_excl + excl_local;
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) {
+        for (int j = 0; j < SPT; ++j) {
             const uint64_t r = r0 + j;
             if (r < A.n_seqs) A.km_off[r] = o;
             o += items[j];
