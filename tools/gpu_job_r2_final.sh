@@ -20,3 +20,11 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mi
 python tools/ncu_phases.py gpurun_out/r2_final_k1.ncu-rep 1e9 > gpurun_out/r2_final_phases.txt 2>&1
 python tools/ncu_lines.py gpurun_out/r2_final_k1.ncu-rep 1e9 40 > gpurun_out/r2_final_kernel_summary.txt 2>&1
 head -3 gpurun_out/r2_final_phases.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1200 python bench.py --workload c5 --no-e2e 2>gpurun_out/r2_c5.err > gpurun_out/r2_config5_sweep.jsonl; echo "c5 rc=$?"
+python tools/c5_table.py gpurun_out/r2_config5_sweep.jsonl
+timeout 300 python tools/bench_fastx.py 2>/dev/null | tee gpurun_out/r2_fastx.jsonl | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print('fastx', d['form'][:40], round(d['Gbp_per_s'], 1), 'Gbp/s')"
+python tools/bench_h64.py 100000 2>&1 | tee gpurun_out/r2_h64.txt
