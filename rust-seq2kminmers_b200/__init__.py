@@ -25,7 +25,7 @@ from typing import Iterator, Optional, Sequence
 import numpy as np
 
 __all__ = [
-    "HashMode", "HashVariant", "KminmerHash", "Kminmer", "KminmersIterator", "KminmersBatch", "Context", "Library",
+    "HashMode", "HashVariant", "KminmerHash", "KminmerVec", "Kminmer", "KminmersIterator", "KminmersBatch", "Context", "Library",
     "S2KError", "NtHashHPCIterator", "NtHashSIMDIterator", "NtHashHPCSIMDIterator", "hpc", "encode_rle",
     "encode_rle_simd", "bounds", "default_library", "LIB_PATH",
 ]
@@ -212,6 +212,15 @@ class KminmersBatch:
         for i in range(a, b):
             yield KminmerHash(int(self.hash[i]), int(self.start[i]), int(self.end[i]), i - a, bool(self.rev[i]))
 
+    def kminmer_vecs(self, r: int, k: int) -> Iterator["KminmerVec"]:
+        """The items of sequence r in the `KminmerVec` flavour (src/kminmer.rs:17-38): every window of k consecutive
+        minimizers as the vector of their hashes, start of the first, end of the last, offset.  Needs the minimizer
+        stream (want_minimizers=True)."""
+        m = self.minimizers_of(r)
+        for c in range(max(0, len(m) - k + 1)):
+            w = m[c:c + k]
+            yield KminmerVec(w["hash"], int(w["start"][0]), int(w["end"][-1]), c)
+
     def minimizers_of(self, r: int) -> np.ndarray:
         """Minimizers of sequence r that feed the window stage (what the reference's inner iterator yields)."""
         if self.minimizers is None:
@@ -243,6 +252,68 @@ class KminmerHash:
 
 
 Kminmer = KminmerHash  # KminmerType, src/lib.rs:39
+
+
+def fxhash64_u32_slice(mers) -> int:
+    """`fxhash::hash64(&Vec<u32>)` (crate fxhash 0.2.1, `Cargo.toml` of the reference; not under /root/reference):
+    FxHasher64 over the slice's `Hash` impl = `write_usize(len)`, then the elements' bytes in one `write` -- eight bytes
+    per step, then four: state = (rotl(state, 5) ^ word) * 0x517cc1b727220a95.  PARITY UNPINNED: the reference holds no
+    vector for it (only `KminmerHash::new`, which the iterator does not call, uses it: src/kminmer.rs:138-161)."""
+    m64, seed = (1 << 64) - 1, 0x517cc1b727220a95
+    h = 0
+
+    def word(h, w):
+        return ((((h << 5) | (h >> 59)) & m64) ^ w) * seed & m64
+    v = [int(x) & 0xffffffff for x in mers]
+    h = word(h, len(v))
+    for i in range(0, len(v) - 1, 2):
+        h = word(h, v[i] | (v[i + 1] << 32))
+    if len(v) & 1:
+        h = word(h, v[-1])
+    return h
+
+
+class KminmerVec:
+    """src/kminmer.rs:17-126: a k-min-mer as the vector of its minimizer hashes, stored in canonical orientation
+    (`normalize`: the reversed vector if it is lexicographically smaller, then rev = True); equality and order by the
+    vector.  Built on the host from the minimizer stream of a batch (KminmersBatch.kminmer_vecs)."""
+
+    def __init__(self, mers, start: int, end: int, offset: int):       # Kminmer::new, src/kminmer.rs:27-38
+        self._mers = [int(x) for x in mers]
+        self.start, self.end, self.offset, self.rev = int(start), int(end), int(offset), False
+        self.normalize()
+
+    def normalize(self):                                               # src/kminmer.rs:53-60
+        r = self._mers[::-1]
+        if r < self._mers:
+            self._mers, self.rev = r, True
+
+    def is_normalized(self) -> bool:                                   # src/kminmer.rs:63-67
+        return self._mers <= self._mers[::-1]
+
+    def mers(self):                                                    # src/kminmer.rs:80-82
+        return list(self._mers)
+
+    def print(self) -> str:                                            # src/kminmer.rs:70-77: first two digits of each hash
+        return "".join(str(x)[:2] + " " for x in self._mers)
+
+    def get_hash_u64(self) -> int:                                     # src/kminmer.rs:90-92
+        return fxhash64_u32_slice(self._mers)
+
+    def to_kminmer_hash(self) -> "KminmerHash":                        # KminmerHash::new, src/kminmer.rs:138-161
+        return KminmerHash(self.get_hash_u64(), self.start, self.end, self.offset, self.rev)
+
+    def __eq__(self, other):
+        return isinstance(other, KminmerVec) and self._mers == other._mers
+
+    def __lt__(self, other):
+        return self._mers < other._mers
+
+    def __hash__(self):
+        return hash(tuple(self._mers))
+
+    def __repr__(self):
+        return f"KminmerVec(mers={self._mers}, start={self.start}, end={self.end}, offset={self.offset}, rev={self.rev})"
 
 
 def _as_u8(seq) -> np.ndarray:

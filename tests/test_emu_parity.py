@@ -237,3 +237,24 @@ def test_h64_flavour_emulated(S, O, emu_ctx, batches, fixture_seq):
     """H = u64: KAT-2 of the reference (tests/main.rs:18-39) through the kernels, closed-form parity."""
     from parity_cases import check_h64_flavour
     check_h64_flavour(S, O, emu_ctx, batches, fixture_seq, scale=1)
+
+
+def test_kminmer_vec_flavour_emulated(S, O, emu_ctx, batches, fixture_seq):
+    """KminmerVec (src/kminmer.rs:17-126) built from the minimizer stream: the same windows as the KminmerHash items
+    (start, end, offset), canonical orientation by lexicographic order of the hash vector."""
+    b = emu_ctx.run(fixture_seq, np.array([0, len(fixture_seq)], dtype=np.uint64), 31, 5, 0.01, S.HashMode.HpcSimd,
+                    want_minimizers=True)
+    vecs, items = list(b.kminmer_vecs(0, 5)), list(b.items(0))
+    assert len(vecs) == len(items) > 1000
+    mins = b.minimizers_of(0)["hash"]
+    n_rev = 0
+    for c, (v, it) in enumerate(zip(vecs, items)):
+        assert (v.start, v.end, v.offset) == (it.start, it.end, it.offset) and v.is_normalized()
+        w = [int(x) for x in mins[c:c + 5]]
+        assert v.mers() == (w[::-1] if v.rev else w) and v.rev == (w[::-1] < w)
+        n_rev += v.rev
+    assert 0 < n_rev < len(vecs)
+    a, r = S.KminmerVec([3, 1, 2], 0, 9, 0), S.KminmerVec([2, 1, 3], 0, 9, 0)
+    assert a == r and a.rev != r.rev and a.mers() == [2, 1, 3] and a.print() == "2 1 3 "
+    assert a.get_hash_u64() == r.get_hash_u64() != S.KminmerVec([2, 1, 4], 0, 9, 0).get_hash_u64()
+    assert sorted([S.KminmerVec([5, 1], 0, 1, 0), S.KminmerVec([1, 2], 0, 1, 1)])[0].mers() == [1, 2]
