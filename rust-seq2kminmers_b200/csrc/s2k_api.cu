@@ -586,7 +586,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         CU(cudaStreamSynchronize(st));
         n_min = hsmall[0];
         const uint32_t errw = (uint32_t)hsmall[2];
-        if (errw & ERR_ALIGN) return fail(ctx, S2K_ERR_INTERNAL, "shared-memory tables are not 256-byte aligned");
+        if (errw & ERR_ALIGN) return fail(ctx, S2K_ERR_INTERNAL, "shared-memory tables are not 256-byte aligned (or a warp of k_minimizers started partial)");
         if (errw & ERR_SPIN) return fail(ctx, S2K_ERR_INTERNAL, "scan look-back timed out");
         if (!(errw & ERR_CAP) && n_min <= cap) break;
         if (getenv("S2K_TRACE_RERUN"))

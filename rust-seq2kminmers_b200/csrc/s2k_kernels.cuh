@@ -208,20 +208,16 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v)
 }
 // Exclusive block scan of one uint32 per thread (NT threads). Returns exclusive prefix; total via out-param.
 // One barrier: the caller hands in a wsum buffer whose previous readers are already behind some other barrier.
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, uint32_t &total)
+__device__ __forceinline__ uint32_t warp_incl_scan_m(uint32_t v, int lane, uint32_t one);
+__device__ __forceinline__ void warp_totals(const uint32_t *wsum, int warp, int lane, uint32_t one, uint32_t &below, uint32_t &all);
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, uint32_t &total, uint32_t one)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = warp_incl_scan(v, lane);
+    uint32_t incl = warp_incl_scan_m(v, lane, one);
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    uint32_t pre = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < NT / 32; ++i) {
-        uint32_t s = wsum[i];
-        if (i < warp) pre += s;
-        tot += s;
-    }
-    total = tot;
+    uint32_t pre;
+    warp_totals(wsum, warp, lane, one, pre, total);
     return pre + incl - v;
 }
 __device__ __forceinline__ uint32_t lowmask(uint32_t n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
@@ -295,6 +291,44 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+#endif
+}
+// warp_incl_scan with its adds on the multiply-add pipe (one = 1 in a register ptxas cannot fold, see k_minimizers)
+__device__ __forceinline__ uint32_t warp_incl_scan_m(uint32_t v, int lane, uint32_t one)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = mad_u32(one, t, v);
+    }
+    return v;
+}
+// The NT / 32 warp totals of a block scan, turned into (sum of the warps below, sum of all) by a scan over lanes 0..7
+// with its adds on the multiply-add pipe -- one shared load, five shuffles and a handful of ALU instructions where the
+// plain loop spends eight loads and sixteen.  S2K_WARP_TOTALS_LOOP restores the loop.
+__device__ __forceinline__ void warp_totals(const uint32_t *wsum, int warp, int lane, uint32_t one, uint32_t &below, uint32_t &all)
+{
+#if defined(S2K_WARP_TOTALS_LOOP) || defined(S2K_EMU)
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) {
+        const uint32_t s = wsum[i];
+        if (i < warp) pre += s;
+        tot += s;
+    }
+    (void)lane; (void)one;
+    below = pre; all = tot;
+#else
+    static_assert(NT / 32 == 8, "warp_totals scans eight totals");
+    const uint32_t x = wsum[lane & 7];
+    uint32_t v = x;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((lane & 7) >= o) v = mad_u32(one, t, v);
+    }
+    all = __shfl_sync(0xffffffffu, v, 7);
+    below = __shfl_sync(0xffffffffu, v - x, warp);
 #endif
 }
 template <bool W31> __device__ __forceinline__ uint32_t rol8(uint32_t x)
@@ -823,7 +857,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
     // one_r is 1 in a register ptxas can neither fold nor re-load from the constant bank (full warps: 32 >> 5).
     const uint32_t one_r = A.one & ((uint32_t)__popc(__activemask()) >> 5);
     const smem_tab_t xft = smem_tab(S.xf);                 // S.lut lies 256 bytes below: one register
-    if (tid == 0 && !smem_tab_ok(xft)) atomicOr(A.err, ERR_ALIGN);
+    if ((tid == 0 && !smem_tab_ok(xft)) || one_r != 1u) atomicOr(A.err, ERR_ALIGN);   // (a partial warp would make one_r 0)
     for (int i = tid; i < (int)sizeof(S.code); i += NT) S.code[i] = ZC8;
     if (tid < 16) S.pre[tid] = ZC8;
     for (int i = tid; i < NCHUNK; i += NT) { S.startw[i] = 0; S.shortw[i] = 0; }
@@ -909,8 +943,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         uint32_t k16[4], st16[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t sw = S.startw[64 * warp + 16 * j + (lane >> 1)];
-            st16[j] = (lane & 1) ? (sw >> 16) : (sw & 0xffffu);
+            st16[j] = reinterpret_cast<const uint16_t *>(S.startw)[128 * warp + 32 * j + lane];   // the piece's half of its chunk word
         }
         if (HPC) {
             // keep bit = byte differs from the byte before it.  Per word: PRMT lines the previous bytes up, XOR, the
@@ -952,7 +985,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // One warp scan per pair of rounds (counts of a round sum to at most 512: 16-bit fields), then the rounds'
         // totals: kept bases before piece (j, lane) = before the warp + rounds below j + lanes below in round j.
         const uint32_t c0 = __popc(k16[0]), c1 = __popc(k16[1]), c2 = __popc(k16[2]), c3 = __popc(k16[3]);
-        const uint32_t i01 = warp_incl_scan(c0 | (c1 << 16), lane), i23 = warp_incl_scan(c2 | (c3 << 16), lane);
+        const uint32_t i01 = warp_incl_scan_m(c0 | (c1 << 16), lane, one_r), i23 = warp_incl_scan_m(c2 | (c3 << 16), lane, one_r);
         const uint32_t t01 = __shfl_sync(0xffffffffu, i01, 31), t23 = __shfl_sync(0xffffffffu, i23, 31);
         uint32_t qj[4];
         qj[0] = (i01 & 0xffffu) - c0;
@@ -964,13 +997,8 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // so the kept count of the halo is published before the scan's only barrier.
         if (warp == 0 && lane == (int)((A.halo >> 4) & 31u)) S.hk = (A.halo >> 9) ? qj[1] : qj[0];
         __syncthreads();
-        uint32_t qw = 0, wk = 0;
-#pragma unroll
-        for (int i = 0; i < NT / 32; ++i) {
-            const uint32_t sw = S.wsum[0][i];
-            if (i < warp) qw += sw;
-            wk += sw;
-        }
+        uint32_t qw, wk;
+        warp_totals(S.wsum[0], warp, lane, one_r, qw, wk);
         {
             uint16_t *kw16 = reinterpret_cast<uint16_t *>(S.keepw);
 #pragma unroll
@@ -1139,7 +1167,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
 #pragma unroll
             for (int x = 0; x < MW; ++x) cnt += __popcll(mask[x]);
             uint32_t tot;
-            const uint32_t ex = block_excl_scan(cnt, S.wsum[1 + pass], tot);
+            const uint32_t ex = block_excl_scan(cnt, S.wsum[1 + pass], tot, one_r);
 #pragma unroll
             for (int x = 0; x < MW; ++x) S.hitw[pass][tid][x] = mask[x];
             S.hitpre[pass][tid] = tile_min + ex;
