@@ -546,8 +546,8 @@ def run_b200(args):
 
 # Figures of the committed ncu capture of the current k_minimizers (profiles/r2_final_kernel_summary.txt, 1.000 Gbp launch)
 NCU_SOURCE = "profiles/r2_final_kernel_summary.txt"
-NCU_DRAM_READ, NCU_DRAM_WRITE = 1.1010e9, 0.3106e9
-NCU_INSTR_PER_BASE, NCU_ALU_SHARE = 30.76, 0.552      # smsp__inst_executed; ALU-class share (profiles/r2_final_phases.txt)
+NCU_DRAM_READ, NCU_DRAM_WRITE = 1.1004e9, 0.3086e9
+NCU_INSTR_PER_BASE, NCU_ALU_SHARE = 30.01, 0.529      # smsp__inst_executed; ALU-class share (profiles/r2_final_phases.txt)
 
 
 def run_c5(B, O, args):
