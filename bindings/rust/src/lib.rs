@@ -32,6 +32,12 @@ impl KminmerHash {
 
 #[repr(C)]
 pub struct S2kParams { pub l: u32, pub k: u32, pub density: f64, pub mode: i32, pub variant: i32 }
+/// `s2k_count_result`: (hash, count, id of the first item) of the distinct k-min-mer hashes, device pointers.
+#[repr(C)]
+pub struct S2kCountResult {
+    pub n_distinct: u64, pub n_items: u64, pub hash: *const u64, pub count: *const u32, pub first: *const u64,
+    pub location: i32, pub reserved: i32,
+}
 
 /// Item of `NtHashHPCIterator` / `NtHashSIMDIterator` / `NtHashHPCSIMDIterator` plus the sequence index.
 #[repr(C)]
@@ -80,6 +86,13 @@ extern "C" {
     pub fn s2k_encode_rle(ctx: *mut S2kCtx, bases: *const u8, seq_off: *const u64, n_seqs: u64,
                           out: *mut S2kRleResult) -> c_int;
     pub fn s2k_bounds(density: f64, bound_scalar: *mut u32, bound_simd: *mut u32, bound_31: *mut u32);
+    pub fn s2k_bound_u64(density: f64) -> u64;
+    pub fn s2k_last_minimizer_hash_hi(ctx: *const S2kCtx, d_hi: *mut *const u32) -> c_int;
+    pub fn s2k_count_device(ctx: *mut S2kCtx, d_hash: *const u64, d_id: *const u64, n_items: u64, id_base: u64,
+                            stream: *mut c_void, out: *mut S2kCountResult) -> c_int;
+    pub fn s2k_count_partition_device(ctx: *mut S2kCtx, d_hash: *const u64, n_items: u64, id_base: u64, n_parts: u32,
+                                      part_counts: *mut u64, d_out_hash: *mut u64, d_out_id: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn s2k_count_part(hash: u64, n_parts: u32) -> u32;
     pub fn s2k_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn s2k_host_free(p: *mut c_void);
     pub fn s2k_last_error(ctx: *const S2kCtx) -> *const c_char;
