@@ -11,7 +11,7 @@ so = np.zeros(len(seqs) + 1, dtype=np.uint64); so[1:] = np.cumsum([len(s) for s 
 # exact-size buffers so that any over-read of the inputs is caught
 bases = bases.copy(); so = so.copy()
 ctx = S.Context(0, S.Library(os.environ['S2K_ASAN_LIB']))
-for mode, var, l in [(3, 0, 31), (1, 0, 31), (2, 0, 31), (0, 0, 31), (3, 1, 31), (1, 0, 255), (0, 0, 200), (3, 0, 1), (1, 0, 1)]:
+for mode, var, l in [(3, 0, 31), (1, 0, 31), (0, 0, 31), (3, 1, 31), (1, 0, 255), (3, 0, 1), (1, 2, 40)]:
     r = ctx.run(bases, so, l, 5, 0.05, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)
     print("ok", mode, var, l, r.n_items)
 ctx.set_slab_bytes(30000)
@@ -20,7 +20,7 @@ h, p, off = ctx.encode_rle(bases, so)
 # device API with S2K_NO_MINIMIZER_STREAM: the window stage and the tail rule read the records in place (tile index walks)
 import ctypes
 so_dev = so.copy()
-for mode, k, d in [(3, 5, 0.05), (3, 12, 0.002), (0, 7, 0.0005)]:
+for mode, k, d in [(3, 5, 0.05), (0, 12, 0.002)]:
     want = ctx.run(bases, so, 31, k, d, S.HashMode(mode))
     rd = ctx.run_device(bases.ctypes.data, so_dev.ctypes.data, len(so) - 1, len(bases), 31, k, d, S.HashMode(mode),
                         no_minimizer_stream=True)
