@@ -276,6 +276,18 @@ static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long 
     __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;
 }
+static inline unsigned atomicMin(unsigned *p, unsigned v)
+{
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+static inline unsigned atomicMax(unsigned *p, unsigned v)
+{
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
 {
     unsigned long long cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
