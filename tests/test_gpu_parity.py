@@ -344,3 +344,23 @@ def test_h64_flavour(S, O, gpu_ctx, batches, fixture_seq):
     """H = u64: KAT-2 of the reference (tests/main.rs:18-39) through the kernels, closed-form parity."""
     from parity_cases import check_h64_flavour
     check_h64_flavour(S, O, gpu_ctx, batches, fixture_seq, scale=4)
+
+
+@pytest.mark.gpu
+def test_one_pass_per_run_at_baseline_densities(S, gpu_ctx):
+    """run_device sizes its buffers from the expected selection rate and reruns a batch whose records overflow them.
+    At BASELINE's densities that must not happen (HPC off at d = 0.01 once overflowed a per-CTA append region on every
+    run and silently doubled the step): one run = 8 kernel launches, in every mode, on 1.2 Gbp of config-2 shaped reads."""
+    import torch
+    L, n = 20000, 60000
+    dev = torch.device("cuda:0")
+    d_bases = torch.empty(L * n, dtype=torch.uint8, device=dev)
+    gpu_ctx.synth_device(0x5EED0005, 0, L * n, d_bases.data_ptr())
+    d_so = (torch.arange(n + 1, dtype=torch.int64, device=dev) * L)
+    torch.cuda.synchronize()
+    for mode in (S.HashMode.HpcSimd, S.HashMode.Simd, S.HashMode.Hpc, S.HashMode.Regular):
+        for d in (0.001, 0.01):
+            for in_place in (True, False):
+                before = gpu_ctx.launch_count
+                r = gpu_ctx.run_device(d_bases.data_ptr(), d_so.data_ptr(), n, n * L, 31, 5, d, mode, no_minimizer_stream=in_place)
+                assert r.n_items > 0 and gpu_ctx.launch_count - before == 8, (mode, d, in_place, gpu_ctx.launch_count - before)
