@@ -72,6 +72,23 @@ def _cases(batches, tmp_path, big):
         p = tmp_path / name
         write_fasta(p, seqs, **kw)
         files.append((p, seqs))
+    # lines whose ends fall where a uniform layout wants them although two of them are not of that width (a short line
+    # and a long one that make up for each other): the probing scan must not take the record for uniform
+    odd = [batches.seq(200), batches.seq(95), batches.seq(64)]
+    text = ""
+    for i, q in enumerate(odd):
+        t = bytes(q).decode()
+        lines = [t[a:a + 10] for a in range(0, len(t), 10)]
+        if i == 0:
+            lines[1:3] = [(lines[1] + lines[2])[:4], (lines[1] + lines[2])[4:]]      # 4 + 16 bases: the same number of bytes
+            lines[3:5] = [(lines[3] + lines[4])[:14], (lines[3] + lines[4])[14:]]    # 14 + 6
+        if i == 1:                                         # "AC\nGTACGTA\n": 9 bases in the 11 bytes of a line, every line end
+            lines[6:7] = [lines[6][:2], lines[6][3:]]      # of the uniform layout in place, one more in between
+            odd[i] = np.frombuffer("".join(lines).encode(), dtype=np.uint8).copy()
+        text += f">odd{i}\n" + "\n".join(lines) + "\n"
+    p = tmp_path / "shifty.fa"
+    p.write_text(text, newline="")
+    files.append((p, odd))
     fq = [s for s in seqs if len(s) > 0]
     p = tmp_path / "reads.fq"
     write_fastq(p, fq, rng)
@@ -88,7 +105,7 @@ def test_fastx_ingest_emulated(S, O, emu_ctx, batches, tmp_path):
         for threads in (1, 3):
             check(S, O, emu_ctx, path, seqs, threads)
         streamed += check_streamed(S, O, emu_ctx, path, seqs, 3) is None
-    assert streamed >= 5                                   # blank.fa has lines of uneven width: materialised after all
+    assert streamed >= 5                                   # blank.fa and shifty.fa have lines of uneven width: materialised after all
     with pytest.raises(S.S2KError) as e:
         emu_ctx.run_fastx(tmp_path / "missing.fa", 2, 31, 5, 0.02, S.HashMode.Hpc)
     assert e.value.status == -8
