@@ -5,6 +5,7 @@
 // order and error behaviour follow the reference:
 //   HashMode                         src/lib.rs:21-27
 //   KminmerHash{hash,start,end,offset,rev}, equality/order on .hash only     src/kminmer.rs:128-135,181-203
+//   KminmerVec{mers,start,end,offset,rev}, canonical vector of minimizer hashes   src/kminmer.rs:17-126
 //   KminmersIterator::new(seq,l,k,density,mode) -> iterator of KminmerHash   src/lib.rs:89,179-270
 //   encode_rle_simd / hpc                                                    src/hpc.rs:28-41,44-147
 // Where the reference panics (unwrap/assert) this wrapper throws s2k::Error carrying the C status code.
@@ -36,6 +37,41 @@ struct KminmerHash {
     bool operator<(const KminmerHash &o) const { return hash < o.hash; }           // src/kminmer.rs:193-197
 };
 using KminmerType = KminmerHash;
+
+// KminmerVec (src/kminmer.rs:17-126): the k-min-mer as the vector of its minimizer hashes in canonical orientation
+// (the reversed vector if it is lexicographically smaller, then rev = true); equality and order by the vector.  Built on
+// the host from the minimizer stream of a result (kminmer_vecs below).
+struct KminmerVec {
+    std::vector<uint32_t> mers_;
+    size_t start = 0, end = 0, offset = 0;
+    bool rev = false;
+    KminmerVec() = default;
+    KminmerVec(const uint32_t *mers, size_t k, size_t start_, size_t end_, size_t offset_)      // Kminmer::new, src/kminmer.rs:27-38
+        : mers_(mers, mers + k), start(start_), end(end_), offset(offset_) { normalize(); }
+    void normalize()                                                                            // src/kminmer.rs:53-60
+    {
+        std::vector<uint32_t> r(mers_.rbegin(), mers_.rend());
+        if (r < mers_) { mers_.swap(r); rev = true; }
+    }
+    bool is_normalized() const { return mers_ <= std::vector<uint32_t>(mers_.rbegin(), mers_.rend()); }   // src/kminmer.rs:63-67
+    std::vector<uint32_t> mers() const { return mers_; }                                        // src/kminmer.rs:80-82
+    bool operator==(const KminmerVec &o) const { return mers_ == o.mers_; }
+    bool operator<(const KminmerVec &o) const { return mers_ < o.mers_; }
+};
+// The items of sequence r of a HOST result that carries the minimizer stream (S2K_WANT_MINIMIZERS), KminmerVec flavour.
+inline std::vector<KminmerVec> kminmer_vecs(const s2k_result &res, uint64_t r, size_t k)
+{
+    std::vector<KminmerVec> out;
+    if (!res.minimizers || res.location != S2K_LOC_HOST) return out;
+    const s2k_minimizer *m = res.minimizers + res.min_off[r];
+    const size_t n = res.min_cnt[r];
+    std::vector<uint32_t> h(k);
+    for (size_t c = 0; c + k <= n; ++c) {
+        for (size_t t = 0; t < k; ++t) h[t] = m[c + t].hash;
+        out.emplace_back(h.data(), k, m[c].start, m[c + k - 1].end, c);
+    }
+    return out;
+}
 
 // One CUDA device + stream + buffers; single-threaded like one iterator (src/main.rs:65-79).
 class Context {

@@ -52,6 +52,22 @@ int main(int argc, char **argv)
             CHECK(c == d);
             CHECK(!a.empty() && !c.empty());
         }
+    {   // H = u64 build of the crate (src/lib.rs:30-32): its golden vector, tests/main.rs:18-39, through the same wrapper
+        const std::vector<uint64_t> hashes = {6097375827354318ull, 5077268723048817ull, 17093614815813553ull, 13932651659877218ull,
+            2254626575123847ull, 4725847317728813ull, 10971942364167709ull, 1406844240705087ull, 15284878278949327ull,
+            13429516156719180ull, 10760699289819902ull, 11244197813995113ull, 6993910349997344ull, 22098843726082404ull,
+            4944933674400292ull, 14212811059278321ull, 9310664830401458ull, 11232758307960192ull, 9720472733789719ull,
+            13210101786532125ull};
+        KminmersIterator iter(ctx, contents.data(), contents.size(), 10, 5, 0.0001, HashMode::Regular, HashVariant::NT1_64);
+        size_t count = 0;
+        for (const KminmerHash &kminmer : iter) { CHECK(count < hashes.size()); CHECK(kminmer.get_hash() == hashes[count]); ++count; }
+        CHECK(count == hashes.size());
+    }
+    {   // KminmerVec (src/kminmer.rs:17-60): canonical orientation, order by the vector
+        const uint32_t a[3] = {3, 1, 2}, b[3] = {2, 1, 3};
+        KminmerVec x(a, 3, 0, 9, 0), y(b, 3, 0, 9, 0);
+        CHECK(x == y && x.rev && !y.rev && x.is_normalized() && x.mers() == std::vector<uint32_t>({2, 1, 3}));
+    }
     try {   // assert!(k<=31), src/nthash_avx512_32.rs:33
         KminmersIterator bad(ctx, contents.data(), contents.size(), 32, 5, 0.01, HashMode::Simd);
         CHECK(false);
