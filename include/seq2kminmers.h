@@ -51,6 +51,13 @@ typedef enum s2k_hash_variant {
                              (the SIMD iterators are 32-bit).  Pinned by the reference's own golden vector for that
                              build, tests/main.rs:18-39.  result.minimizers[i].hash then holds the LOW half of the
                              minimizer's hash; s2k_last_minimizer_hash_hi gives the high halves. */
+    ,
+    S2K_HASH_NT1_16 = 3   /* the crate built with `pub type H = u16` (src/lib.rs:29): bound = (density * u16::MAX as f64)
+                             as u16 (src/lib.rs:91), `hash <= bound`, MixHash<u16> = the murmur-style mix of
+                             src/lib.rs:142-155.  Mode Hpc: ntHash1 on a 16-bit state, seeds `as u16`
+                             (src/nthash_hpc.rs:30-49).  Mode Regular: the nthash32 hash truncated, `x as H`
+                             (src/lib.rs:224).  Modes Regular and Hpc only (the SIMD iterators take a u32 bound).
+                             Parity unpinned: the reference holds no vector for this build. */
 } s2k_hash_variant;
 
 /* Status codes.  The reference panics (unwrap/assert) where these are returned:
