@@ -16,7 +16,7 @@ pub enum HashMode { Regular = 0, Hpc = 1, Simd = 2, HpcSimd = 3 }
 /// Which rolling hash: ntHash1-32 (what the crate compiles) or the 31-bit hybrid of `src/nthash2_avx512_32.rs`.
 #[repr(i32)]
 #[derive(Clone, Copy, Debug, PartialEq, Eq)]
-pub enum HashVariant { Nt1_32 = 0, Nt2_31 = 1, Nt1_64 = 2 }
+pub enum HashVariant { Nt1_32 = 0, Nt2_31 = 1, Nt1_64 = 2, Nt1_16 = 3 }
 
 /// `KminmerHash` (`src/kminmer.rs:128-135`); equality and order by `hash` only (`src/kminmer.rs:181-203`).
 #[derive(Clone, Copy, Debug)]
@@ -87,6 +87,7 @@ extern "C" {
                           out: *mut S2kRleResult) -> c_int;
     pub fn s2k_bounds(density: f64, bound_scalar: *mut u32, bound_simd: *mut u32, bound_31: *mut u32);
     pub fn s2k_bound_u64(density: f64) -> u64;
+    pub fn s2k_bound_u16(density: f64) -> u32;
     pub fn s2k_last_minimizer_hash_hi(ctx: *const S2kCtx, d_hi: *mut *const u32) -> c_int;
     pub fn s2k_count_device(ctx: *mut S2kCtx, d_hash: *const u64, d_id: *const u64, n_items: u64, id_base: u64,
                             stream: *mut c_void, out: *mut S2kCountResult) -> c_int;

@@ -224,6 +224,8 @@ int s2k_synth_device(s2k_ctx *ctx, uint64_t seed, uint64_t first, uint64_t count
 void s2k_bounds(double density, uint32_t *bound_scalar, uint32_t *bound_simd, uint32_t *bound_31);
 /* ... and with H = u64 (src/lib.rs:91): (density * (u64::MAX as f64)) as u64, saturating. */
 uint64_t s2k_bound_u64(double density);
+/* The same for H = u16 (S2K_HASH_NT1_16): ((density as f64) * (u16::MAX as f64)) as u16, src/lib.rs:91. */
+uint32_t s2k_bound_u16(double density);
 /* After a DEVICE run with S2K_HASH_NT1_64: device pointer to the high 32 bits of every minimizer's hash, index-aligned
  * with result.minimizers (valid until the next run on the context); NULL after any other run. */
 int s2k_last_minimizer_hash_hi(const s2k_ctx *ctx, const uint32_t **d_hi);

@@ -21,7 +21,7 @@
 namespace s2k {
 
 enum class HashMode : int { Regular = 0, Hpc = 1, Simd = 2, HpcSimd = 3 };
-enum class HashVariant : int { NT1_32 = 0, NT2_31 = 1, NT1_64 = 2 };
+enum class HashVariant : int { NT1_32 = 0, NT2_31 = 1, NT1_64 = 2, NT1_16 = 3 };
 
 struct Error : std::runtime_error {
     int status;

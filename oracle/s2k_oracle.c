@@ -487,12 +487,16 @@ long s2k_oracle_kminmers(const uint8_t *seq, size_t n, int l, int k, double dens
 /* st[] = run starts, c[] = bytes at run starts; fh/rh by direct XOR over the l-mer.
  * width = 32 (nt1), 31 (nt2) or 64 (H=u64, used only to reproduce the reference's u64 golden vectors:
  * tests/main.rs:18-39 and src/old/nthash_hpc.rs.opt4:90-97).  strict: 0 -> `<=`, 1 -> `<`.
+ * width = 16: the crate built with `pub type H = u16` (src/lib.rs:29), 16-bit ntHash1 state of NtHashHPCIterator
+ * (seeds `as u16`, src/nthash_hpc.rs:30-49; u16 rotations); width = 3216: that build in mode Regular, where the
+ * 32-bit nthash32 hash is truncated, `x as H` (src/lib.rs:224), before `hash <= bound`.  Parity unpinned for both:
+ * the reference holds no vector for H = u16.
  * Output hashes are u64 so that width 64 fits. */
 static inline uint64_t rolw(uint64_t x, unsigned r, int w)
 {
     if (w == 64) return rol64(x, r);
     r %= (unsigned)w;
-    uint64_t m = (w == 32) ? 0xffffffffULL : 0x7fffffffULL;
+    uint64_t m = (w == 32) ? 0xffffffffULL : (w == 16) ? 0xffffULL : 0x7fffffffULL;
     return r ? (((x << r) | (x >> (w - r))) & m) : x;
 }
 long s2k_oracle_closed_minimizers(const uint8_t *seq, size_t n, int l, int hpc, int simd_tables, int width,
@@ -512,6 +516,8 @@ long s2k_oracle_closed_minimizers(const uint8_t *seq, size_t n, int l, int hpc, 
         if (last_rule == 1) last = S - 1;
         else if (last_rule == 2 && S > 16 && S % 16 == 0) last = S - 16;
         int shift = width == 31 ? 33 : 0;
+        const int trunc16 = width == 3216;
+        if (trunc16) width = 32;
         for (size_t p = 0; p < last; p++) {
             uint64_t fh = 0, rh = 0;
             for (int i = 0; i < l; i++) {
@@ -523,10 +529,12 @@ long s2k_oracle_closed_minimizers(const uint8_t *seq, size_t n, int l, int hpc, 
                     if (width == 32) { hv &= 0xffffffffULL; rv &= 0xffffffffULL; }
                 } else if (width == 64) { hv = H_LOOKUP64[b]; rv = RC_LOOKUP64[b]; }
                 else { hv = H_LOOKUP[b]; rv = RC_LOOKUP[b]; }
+                if (width == 16) { hv &= 0xffffULL; rv &= 0xffffULL; }
                 fh ^= rolw(hv, (unsigned)(l - 1 - i), width);
                 rh ^= rolw(rv, (unsigned)i, width);
             }
             uint64_t h = fh < rh ? fh : rh;
+            if (trunc16) h &= 0xffffULL;
             int sel = strict ? (h < bound) : (h <= bound);
             if (!sel) continue;
             if ((size_t)cnt < cap) {
@@ -540,7 +548,16 @@ long s2k_oracle_closed_minimizers(const uint8_t *seq, size_t n, int l, int hpc, 
     free(st);
     return cnt;
 }
-/* Closed-form window stage (Appendix A.2) with identity or xorshift mix. */
+/* Closed-form window stage (Appendix A.2).  mix_u32: 0 = identity (MixHash<u64>), 1 = xorshift (MixHash<u32>),
+ * 2 = MixHash<u16> (src/lib.rs:142-155; wrapping multiplies as in a release build). */
+static inline uint64_t mix16(uint16_t h)
+{
+    uint64_t x = h;
+    x ^= rol64(x, 33); x *= 0xff51afd7ed558ccdULL;
+    x ^= rol64(x, 33); x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= rol64(x, 33);
+    return x;
+}
 long s2k_oracle_closed_windows(const uint64_t *mhash, size_t nmin, int k, int mix_u32,
                                uint64_t *hash, uint8_t *rev, size_t cap)
 {
@@ -549,7 +566,7 @@ long s2k_oracle_closed_windows(const uint64_t *mhash, size_t nmin, int k, int mi
     for (size_t c = 0; c + (size_t)k <= nmin; c++) {
         uint64_t f = 0, r = 0;
         for (int t = 0; t < k; t++) {
-            uint64_t m = mix_u32 ? mix32((uint32_t)mhash[c + t]) : mhash[c + t];
+            uint64_t m = mix_u32 == 2 ? mix16((uint16_t)mhash[c + t]) : mix_u32 ? mix32((uint32_t)mhash[c + t]) : mhash[c + t];
             f ^= rol64(m, (unsigned)(k - 1 - t));
             r ^= rol64(m, (unsigned)t);
         }

@@ -45,10 +45,12 @@ class HashMode(enum.IntEnum):
 
 class HashVariant(enum.IntEnum):
     """NT1_32: src/nthash_avx512_32.rs / src/nthash_hpc.rs; NT2_31: src/nthash2_avx512_32.rs; NT1_64: the crate built
-    with `pub type H = u64` (src/lib.rs:30-32; modes Regular and Hpc; golden vector tests/main.rs:18-39)."""
+    with `pub type H = u64` (src/lib.rs:30-32; modes Regular and Hpc; golden vector tests/main.rs:18-39); NT1_16: the
+    crate built with `pub type H = u16` (src/lib.rs:29; modes Regular and Hpc; parity unpinned)."""
     NT1_32 = 0
     NT2_31 = 1
     NT1_64 = 2
+    NT1_16 = 3
 
 
 class S2KError(RuntimeError):
@@ -90,7 +92,7 @@ ABI_SYMBOLS = (
     "s2k_launch_count", "s2k_ctx_set_timing", "s2k_last_kernel_ms", "s2k_synth_device",
     "s2k_ctx_set_slab_bytes", "s2k_run_fastx", "s2k_last_fastx", "s2k_ctx_set_transport",
     "s2k_last_transport", "s2k_run_packed2", "s2k_pack2", "s2k_count_device", "s2k_count_partition_device", "s2k_count_part",
-    "s2k_bound_u64", "s2k_last_minimizer_hash_hi",
+    "s2k_bound_u64", "s2k_last_minimizer_hash_hi", "s2k_bound_u16",
 )
 
 
@@ -119,6 +121,8 @@ class Library:
         L.s2k_encode_rle.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(_RleResult)]
         L.s2k_bound_u64.restype = C.c_uint64
         L.s2k_bound_u64.argtypes = [C.c_double]
+        L.s2k_bound_u16.restype = C.c_uint32
+        L.s2k_bound_u16.argtypes = [C.c_double]
         L.s2k_last_minimizer_hash_hi.restype = C.c_int
         L.s2k_last_minimizer_hash_hi.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.s2k_bounds.restype = None
@@ -606,3 +610,86 @@ def encode_rle(seq, ctx: Optional[Context] = None):
 def hpc(seq, ctx: Optional[Context] = None) -> bytes:
     """src/hpc.rs:28."""
     return encode_rle_simd(seq, ctx)[0]
+
+
+# ------------------------------------------------------------------------------------------------ minimizer TSV
+# src/old/kminmers-readwrite.rs ("written by Baris but unused so far"): the minimizers of one sequence persisted as
+# `position \t hash` lines in `{prefix}-{l}-{density}.mers`, and the k-min-mers (KminmerVec flavour) rebuilt from that
+# file without the sequence.  Host side only; the minimizers themselves come from the device.
+def _rust_display_f64(x: float) -> str:
+    """`format!("{}", x)` for an f64: shortest round-trip digits, never an exponent, no trailing ".0"."""
+    import decimal
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "inf" if x > 0 else "-inf"
+    s = format(decimal.Decimal(repr(x)), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    return "-0" if s in ("-0", "-") else s
+
+
+def mers_path(prefix: str, l: int, density: float) -> str:
+    """src/old/kminmers-readwrite.rs:21,120."""
+    return f"{prefix}-{int(l)}-{_rust_display_f64(density)}.mers"
+
+
+class KminmersWriteIterator:
+    """src/old/kminmers-readwrite.rs:5-104: iterate the k-min-mers (KminmerVec) of `seq` and leave its minimizers in
+    `{prefix}-{l}-{density}.mers`, one `position \\t hash` line each.  hpc=True runs mode Hpc (position = start of the
+    minimizer in original coordinates), hpc=False mode Regular, whose positions the reference writes 1-based
+    (`self.seq_pos += 1; j = self.seq_pos`, :88-89).  The device yields all minimizers of the sequence at once, so the
+    file is complete when the constructor returns (the reference appends while it iterates); selection follows the
+    chosen `variant` (the historical file used a u64 bound with `<`)."""
+
+    def __init__(self, seq, l: int, k: int, density: float, hpc: bool, prefix: str, ctx: Optional["Context"] = None,
+                 variant: HashVariant = HashVariant.NT1_32):
+        s = _as_u8(seq)
+        ctx = ctx or _default_ctx()
+        self.l, self.k, self.path = int(l), int(k), mers_path(prefix, l, density)
+        mode = HashMode.Hpc if hpc else HashMode.Regular
+        b = ctx.run(s, np.array([0, s.shape[0]], dtype=np.uint64), l, k, density, mode, variant, want_minimizers=True)
+        m = b.minimizers_of(0)
+        self._pos = m["start"].astype(np.int64) + (0 if hpc else 1)
+        self._hash = m["hash"].astype(np.uint64)
+        with open(self.path, "w") as f:                                # truncate(true), :22-27
+            f.write("".join(f"{int(p)}\t{int(h)}\n" for p, h in zip(self._pos, self._hash)))
+        self._c = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> "KminmerVec":
+        c, k = self._c, self.k
+        if c + k > len(self._pos):
+            raise StopIteration
+        self._c += 1
+        return KminmerVec(self._hash[c:c + k], int(self._pos[c]), int(self._pos[c + k - 1]) + self.l - 1, c)   # :93
+
+
+class KminmersReadIterator:
+    """src/old/kminmers-readwrite.rs:107-165: the same k-min-mers from the `.mers` file alone."""
+
+    def __init__(self, l: int, k: int, density: float, prefix: str):
+        self.l, self.k = int(l), int(k)
+        self._f = open(mers_path(prefix, l, density), "r")             # "Could not open minimizer index."
+        self._pos, self._sk, self._count = [], [], 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> "KminmerVec":
+        while True:
+            line = self._f.readline()
+            if not line:
+                self._f.close()
+                raise StopIteration
+            v = line.rstrip("\n").split("\t")
+            self._pos.append(int(v[0]))
+            self._sk.append(int(v[1]))
+            if len(self._sk) == self.k:
+                km = KminmerVec(self._sk, self._pos[0], self._pos[self.k - 1] + self.l - 1, self._count)
+                self._sk, self._pos = self._sk[1:], self._pos[1:]
+                self._count += 1
+                return km

@@ -248,6 +248,8 @@ struct Plan {
     bool hpc, simd, w31, quirk;
     bool h64 = false;            // H = u64 flavour (S2K_HASH_NT1_64): 64-bit ntHash1, `hash <= bound` on 64 bits
     uint64_t thr64 = 0;
+    bool h16 = false;            // H = u16 flavour (S2K_HASH_NT1_16): see make_plan
+    bool trunc16 = false;        //   ... in mode Regular: 32-bit hash truncated before the test
     uint4 xy64[XYN];
     uint32_t l, k, d, need, thr, halo, tile;
     bool none;       // threshold selects nothing
@@ -262,7 +264,8 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
 {
     if (!p) return fail(ctx, S2K_ERR_NULL, "params is null");
     if (p->mode < S2K_MODE_REGULAR || p->mode > S2K_MODE_HPCSIMD) return fail(ctx, S2K_ERR_BAD_PARAM, "unknown hash mode");
-    if (p->variant != S2K_HASH_NT1_32 && p->variant != S2K_HASH_NT2_31 && p->variant != S2K_HASH_NT1_64)
+    if (p->variant != S2K_HASH_NT1_32 && p->variant != S2K_HASH_NT2_31 && p->variant != S2K_HASH_NT1_64 &&
+        p->variant != S2K_HASH_NT1_16)
         return fail(ctx, S2K_ERR_BAD_PARAM, "unknown hash variant");
     if (p->l == 0 || p->k == 0) return fail(ctx, S2K_ERR_BAD_PARAM, "l and k must be >= 1");
     P.hpc = p->mode == S2K_MODE_HPC || p->mode == S2K_MODE_HPCSIMD;
@@ -271,6 +274,9 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     if (P.w31 && !P.simd) return fail(ctx, S2K_ERR_BAD_PARAM, "the 31-bit variant replaces the SIMD iterator only (modes Simd/HpcSimd)");
     P.h64 = p->variant == S2K_HASH_NT1_64;
     if (P.h64 && P.simd) return fail(ctx, S2K_ERR_BAD_PARAM, "H = u64 exists for the scalar iterators only (modes Regular/Hpc): the SIMD iterators are 32-bit (src/nthash_avx512_32.rs)");
+    P.h16 = p->variant == S2K_HASH_NT1_16;
+    if (P.h16 && P.simd) return fail(ctx, S2K_ERR_BAD_PARAM, "H = u16 exists for the scalar iterators only (modes Regular/Hpc): the SIMD iterators take a u32 bound (src/nthash_avx512_32.rs:32)");
+    P.trunc16 = P.h16 && !P.hpc;
     if (P.simd && p->l > 31) return fail(ctx, S2K_ERR_L_TOO_BIG, "l must be <= 31 in the Simd/HpcSimd modes");
     if (!P.simd && p->l >= 256) return fail(ctx, S2K_ERR_L_TOO_BIG, "l must be < 256 in the Regular/Hpc modes");
     if (p->k > 0x7fffffffu) return fail(ctx, S2K_ERR_BAD_PARAM, "k too large");
@@ -292,6 +298,17 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         P.none = false;                              // `hash <= 0` still selects a hash of 0
         P.dense = (double)P.thr64 / 18446744073709551616.0 >= 0.0027;
     }
+    if (P.h16) {
+        // src/lib.rs:91 with H = u16.  Mode Hpc (src/nthash_hpc.rs with 16-bit seeds and rotations): the state lives
+        // DUPLICATED in both halves of a 32-bit word -- a 32-bit rotation of x * 0x10001 is the 16-bit rotation of x,
+        // duplicated; XOR keeps the form; x -> x * 0x10001 is increasing, so min and `<=` agree with the 16-bit ones.
+        // The 32-bit kernels run unchanged on duplicated seeds and a duplicated bound; k_finalize masks the records.
+        // Mode Regular (`hash = x as H`, src/lib.rs:224): 32-bit tables, truncation inside the byte-form hash stage.
+        const uint32_t b16 = s2k_bound_u16(p->density);
+        P.thr = P.trunc16 ? b16 : b16 * 0x10001u;
+        P.none = false;
+        P.dense = ((double)b16 + 1.0) / 65536.0 >= (P.trunc16 ? 0.0054 : 0.0027);   // truncation: no doubling by the minimum
+    }
     // base classes: 0..3 = A C T G (bits 1-2 of the ASCII byte: the packed compaction classifies with one AND),
     // 4 = seed 0, 5 = seed 1.  SEED64 is in the order A C G T; the complement of seed s is seed 3 - s.
     const int w = P.w31 ? 31 : 32;
@@ -302,6 +319,7 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
         rc[b] = P.w31 ? (uint32_t)(SEED64[3 - seed_of[b]] >> 33) : (uint32_t)SEED64[3 - seed_of[b]];
     }
     h[5] = rc[5] = 1;
+    if (P.h16 && !P.trunc16) for (int b = 0; b < 6; ++b) { h[b] = (h[b] & 0xffffu) * 0x10001u; rc[b] = (rc[b] & 0xffffu) * 0x10001u; }
     static const uint8_t code_of[6] = {0, 8, 16, 24, 32, 40};     // see s2k_kernels.cuh (table layout)
     if (P.simd) {                                    // low nibble, src/nthash_avx512_32.rs:178-193
         static const uint8_t nib[16] = {4, 0, 4, 1, 2, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4};
@@ -384,7 +402,7 @@ void timing_prepare(s2k_ctx *ctx)
 int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, uint64_t n_seqs, uint64_t n_bases,
                const Plan &P, cudaStream_t st, s2k_result *out, bool in_place_ok = false)
 {
-    const bool in_place = in_place_ok && (ctx->flags & S2K_NO_MINIMIZER_STREAM) && P.k <= (uint32_t)KW_MAX && !P.h64;
+    const bool in_place = in_place_ok && (ctx->flags & S2K_NO_MINIMIZER_STREAM) && P.k <= (uint32_t)KW_MAX && !P.h64 && !P.h16;
     ctx->min_hi_valid = false;
     int rc;
     if ((rc = set_attrs(ctx)) != S2K_OK) return rc;
@@ -488,6 +506,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         A.n_seqs = n_seqs; A.n_bases = n_bases; A.n_tiles = n_tiles;
         A.tile = (uint32_t)tile_eff; A.halo = P.halo; A.l = P.l; A.d = P.d; A.need = P.need; A.thr = P.thr;
         A.vmask = P.simd ? 0x0f0f0f0fu : 0xffffffffu; A.one = 1u;
+        A.trunc16 = P.trunc16 ? 1u : 0u;
         A.thr64 = P.thr64; A.min_hi = P.h64 ? ptr<uint32_t>(ctx->d_tmp_hi) : nullptr;
         if (P.h64) std::memcpy(A.xy64, P.xy64, sizeof(P.xy64)); else std::memset(A.xy64, 0, sizeof(A.xy64));
         std::memcpy(A.cls_lut, P.lut, 256);
@@ -520,6 +539,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         F.tile_pre = ptr<ulonglong2>(ctx->d_tile_pre);
         F.tile_src = in_place ? ptr<ulonglong2>(ctx->d_tile_src) : nullptr; F.copy = in_place ? 0 : 1;
         F.tmp_hi = P.h64 ? ptr<uint32_t>(ctx->d_tmp_hi) : nullptr; F.mins_hi = P.h64 ? ptr<uint32_t>(ctx->d_mins_hi) : nullptr;
+        F.hmask = P.h16 ? 0xffffu : 0xffffffffu;
         F.err = A.err;
         const int gridf = (int)std::min<uint64_t>(((uint64_t)n_tiles + 8) / 8, (uint64_t)ctx->sm_count * 8);
         S2K_LAUNCH(k_finalize, gridf, 256, 0, st, false, F);
@@ -557,6 +577,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         C.hash = ptr<uint64_t>(ctx->d_hash); C.start = ptr<uint32_t>(ctx->d_start);
         C.end = ptr<uint32_t>(ctx->d_end); C.rev = ptr<uint8_t>(ctx->d_rev);
         C.hash_hi = P.h64 ? ptr<uint32_t>(ctx->d_mins_hi) : nullptr;
+        C.mix16 = P.h16 ? 1u : 0u;
         if (in_place) {
             K3TArgs D;
             D.W = C; D.tile_info = ptr<uint4>(ctx->d_tile_info); D.tile_src = B.tile_src; D.n_tiles = n_tiles;
@@ -569,7 +590,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
             }
         } else {
             const int g3 = (int)std::min<uint64_t>((item_cap + 255) / 256, (uint64_t)ctx->sm_count * 16);
-            switch (P.k <= (uint32_t)KW_MAX && !P.h64 ? (int)P.k : 0) {
+            switch (P.k <= (uint32_t)KW_MAX && !P.h64 && !P.h16 ? (int)P.k : 0) {
 #define S2K_WINDOWS_CASE(K) case K: S2K_LAUNCH(k_windows_w<K>, g3, 256, 0, st, false, C); break;
                 S2K_WINDOWS_CASE(1) S2K_WINDOWS_CASE(2) S2K_WINDOWS_CASE(3) S2K_WINDOWS_CASE(4) S2K_WINDOWS_CASE(5) S2K_WINDOWS_CASE(6)
                 S2K_WINDOWS_CASE(7) S2K_WINDOWS_CASE(8) S2K_WINDOWS_CASE(9) S2K_WINDOWS_CASE(10) S2K_WINDOWS_CASE(11) S2K_WINDOWS_CASE(12)
@@ -660,6 +681,13 @@ uint64_t s2k_bound_u64(double density)
     if (!(v > 0.0)) return 0ull;
     if (v >= 18446744073709551616.0) return ~0ull;           // Rust `as` saturates
     return (uint64_t)v;
+}
+uint32_t s2k_bound_u16(double density)
+{
+    const double v = density * 65535.0;                      // ((density as f64) * (u16::MAX as f64)) as u16
+    if (!(v > 0.0)) return 0u;
+    if (v >= 65535.0) return 0xffffu;                        // Rust `as` saturates
+    return (uint32_t)v;
 }
 int s2k_last_minimizer_hash_hi(const s2k_ctx *ctx, const uint32_t **d_hi)
 {

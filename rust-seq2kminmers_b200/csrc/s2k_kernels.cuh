@@ -125,6 +125,10 @@ struct K1Args {
     uint4     xy64[XYN];
     uint64_t  thr64;
     uint32_t *min_hi;
+    // H = u16 flavour (src/lib.rs:29), mode Regular: the 32-bit canonical hash is truncated before the test (`x as H`,
+    // src/lib.rs:224) -- byte form of the tile only.  (Mode Hpc of that flavour needs nothing here: a 16-bit state
+    // duplicated in both halves of the word rotates, XORs and compares like the 32-bit one; see make_plan.)
+    uint32_t  trunc16;
 };
 
 struct Smem {
@@ -399,7 +403,7 @@ __device__ __forceinline__ int64_t pos_in_chunk(const Smem &S, int64_t W0, int c
 // cb[i-l] = the base leaving the window.  Selected owners: bit i of mask, hash to hs[i].
 //
 // hash_owners_bytes: any classes.  Per owner two byte loads, one IMAD (8*out+in), one 8-byte load from xy.
-template <bool W31>
+template <bool W31, bool T16 = false>
 __device__ __forceinline__ void hash_owners_bytes(const Smem &S, const uint8_t *cb, int l, uint32_t thr, uint32_t *hs,
                                                   unsigned long long (&mask)[MW])
 {
@@ -415,7 +419,7 @@ __device__ __forceinline__ void hash_owners_bytes(const Smem &S, const uint8_t *
         const uint2 tt = xy_at(S, i > 0 ? (uint32_t)co[i] : (uint32_t)ZC8, cb[i]);
         fh = rol1<W31>(fh) ^ tt.x;
         rh = ror1<W31>(rh) ^ tt.y;
-        const uint32_t hv = min(fh, rh);
+        const uint32_t hv = T16 ? (min(fh, rh) & 0xffffu) : min(fh, rh);
         if (hv <= thr) { mask[i >> 6] |= 1ull << (i & 63); hs[i] = hv; }
     }
 }
@@ -1019,7 +1023,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         // to the byte form after the barrier.
         const uint32_t hk_real = S.hk;
         const bool need_walk = HPC && (int64_t)S.s0 < W0 && hk_real < A.need;
-        const bool try_packed = !H64 && !need_walk && l <= PK_LMAX;
+        const bool try_packed = !H64 && !need_walk && l <= PK_LMAX && !A.trunc16;
         if (try_packed) {
             if (compact_packed(S, w, k16, qj, A.vmask)) S.rare = 1u;
         } else {
@@ -1150,6 +1154,8 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                     const uint8_t *cb = S.code + XB + hk + v0 - d; // cb[i]: last base of owner i's l-mer; 4-aligned
                     if (H64) {
                         hash_owners_bytes64(S, cb, l, A.thr64, hs + v0, mask);
+                    } else if (!W31 && A.trunc16) {
+                        hash_owners_bytes<false, true>(S, cb, l, A.thr, hs + v0, mask);
                     } else {
                         const uint32_t rare = hash_owners_words<W31, DENSE>(S, xft, cb, l, A.thr, hs + v0, mask);
                         if (rare & RARE4) {                        // a rare class among the bytes touched: redo via xy
@@ -1377,6 +1383,7 @@ struct KFArgs {
     const uint32_t *tmp_hi;      // H = u64 flavour: high halves of the hashes, beside tmp / mins (else null)
     uint32_t *mins_hi;
     int32_t copy;                // 0: leave the records where they are (the window stage reads them through tile_src)
+    uint32_t hmask;              // AND-ed into the hash of every copied record (0xffff for the H = u16 flavour, else ~0)
     const uint32_t *err;         // ERR_CAP set: the record store overflowed, the host reruns -- touch nothing
 };
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs A)
@@ -1401,7 +1408,9 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ KFArgs
         }
         if (A.copy && src + info.x <= A.min_cap)
             for (uint32_t j = lane; j < info.x; j += 32) {
-                A.mins[bm + j] = A.tmp[src + j];
+                uint4 rec = A.tmp[src + j];
+                rec.x &= A.hmask;
+                A.mins[bm + j] = rec;
                 if (A.tmp_hi) A.mins_hi[bm + j] = A.tmp_hi[src + j];
             }
     }
@@ -1702,11 +1711,20 @@ struct K3Args {
     uint32_t *start, *end;
     uint8_t  *rev;
     const uint32_t *hash_hi;              // H = u64 flavour (k_windows only): high halves, MixHash<u64> = identity (src/lib.rs:171-177)
+    uint32_t mix16;                       // H = u16 flavour (k_windows only): MixHash<u16>, src/lib.rs:142-155
 };
 __device__ __forceinline__ uint64_t mix32(uint32_t h)      // MixHash for u32, src/lib.rs:157-169
 {
     uint64_t x = h;
     x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    return x;
+}
+__device__ __forceinline__ uint64_t mix16(uint32_t h)      // MixHash for u16, src/lib.rs:142-155 (wrapping multiplies)
+{
+    uint64_t x = h & 0xffffu;
+    x ^= (x << 33) | (x >> 31); x *= 0xff51afd7ed558ccdull;
+    x ^= (x << 33) | (x >> 31); x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= (x << 33) | (x >> 31);
     return x;
 }
 __device__ __forceinline__ uint64_t rol64(uint64_t x, uint32_t r)
@@ -1729,7 +1747,7 @@ __global__ void __launch_bounds__(256) k_windows(const __grid_constant__ K3Args 
         uint32_t end = first.z;
         for (uint32_t tt = 0; tt < A.k; ++tt) {
             const uint4 mrec = tt ? A.mins[g + tt] : first;
-            const uint64_t m = A.hash_hi ? ((uint64_t)A.hash_hi[g + tt] << 32 | mrec.x) : mix32(mrec.x);
+            const uint64_t m = A.hash_hi ? ((uint64_t)A.hash_hi[g + tt] << 32 | mrec.x) : A.mix16 ? mix16(mrec.x) : mix32(mrec.x);
             f ^= rol64(m, A.k - 1 - tt);
             r ^= rol64(m, tt);
             end = mrec.z;

@@ -181,3 +181,49 @@ def check_h64_flavour(S, O, ctx, B, fixture_seq, scale=1):
                 assert np.array_equal(got.end[a:e], en[k - 1:].astype(np.uint32)), (mode, l, k, d, r)
     with pytest.raises(S.S2KError):                    # the SIMD iterators are 32-bit
         ctx.run(b1, so1, 10, 3, 0.01, S.HashMode.HpcSimd, V)
+
+
+def check_h16_flavour(S, O, ctx, B, fixture_seq, scale=1):
+    """S2K_HASH_NT1_16 (the crate built with `pub type H = u16`, src/lib.rs:29): items against the oracle's closed form
+    -- mode Hpc: 16-bit ntHash1 state (seeds `as u16`, src/nthash_hpc.rs:30-49); mode Regular: the nthash32 hash
+    truncated (`x as H`, src/lib.rs:224); `hash <= (density * u16::MAX as f64) as u16` (src/lib.rs:91); MixHash<u16>
+    (src/lib.rs:142-155).  Parity unpinned (no reference-held vector for this build); tied to the pinned 32-bit profile
+    at density 1: the Regular minimizer hashes must be the low halves of the 32-bit ones (KAT-1's build)."""
+    V = S.HashVariant.NT1_16
+    lens = [0, 5, 11, 12, 40, 300, 0, 2500, 16000 * scale, 33, 64, 65]
+    b1, so1 = B.batch(lens, runp=0.3)
+    b2, so2 = B.batch([4000, 100, 9000], alphabet=b"ACGTNacgtXRY", runp=0.2)
+    fx = np.frombuffer(bytes(fixture_seq), dtype=np.uint8)[:30000]
+    b3, so3 = fx, np.array([0, len(fx)], dtype=np.uint64)
+    for bases, so in ((b1, so1), (b2, so2), (b3, so3)):
+        for mode, l, k, d in ((REG, 10, 5, 0.01), (HPC, 10, 3, 0.02), (REG, 31, 2, 0.05), (HPC, 31, 5, 0.05),
+                              (HPC, 64, 2, 0.1), (REG, 100, 1, 0.3), (HPC, 11, 4, 1.0), (REG, 17, 3, 0.0),
+                              (HPC, 16, 2, 0.01), (HPC, 33, 3, 0.004), (REG, 31, 5, 0.01)):
+            got = ctx.run(bases, so, l, k, d, S.HashMode(mode), V, want_minimizers=True)
+            bound = min(int(d * 65535.0), 65535)
+            hpc = mode == HPC
+            for r in range(len(so) - 1):
+                seq = bases[int(so[r]):int(so[r + 1])]
+                st, en, h = O.closed_minimizers(seq, l, hpc, False, 16 if hpc else 3216, bound, False,
+                                                1 if hpc else 0, 1 if hpc else 0)
+                m0, m1 = int(got.min_off[r]), int(got.min_off[r + 1])
+                assert m1 - m0 == len(h), (mode, l, k, d, r, m1 - m0, len(h))
+                assert np.array_equal(got.minimizers["hash"][m0:m1], h.astype(np.uint32)), (mode, l, k, d, r)
+                a, e = int(got.km_off[r]), int(got.km_off[r + 1])
+                if len(h) < k:
+                    assert e == a, (mode, l, k, d, r)
+                    continue
+                wh, wr = O.closed_windows(h, k, mix_u32=2)
+                assert e - a == len(wh), (mode, l, k, d, r, e - a, len(wh))
+                assert np.array_equal(got.hash[a:e], wh) and np.array_equal(got.rev[a:e], wr), (mode, l, k, d, r)
+                assert np.array_equal(got.start[a:e], st[:len(wh)].astype(np.uint32)), (mode, l, k, d, r)
+                assert np.array_equal(got.end[a:e], en[k - 1:].astype(np.uint32)), (mode, l, k, d, r)
+    # density 1: every l-mer is selected in both builds, so the u16 Regular stream is the u32 one truncated
+    g16 = ctx.run(b2, so2, 12, 3, 1.0, S.HashMode.Regular, V, want_minimizers=True)
+    g32 = ctx.run(b2, so2, 12, 3, 1.0, S.HashMode.Regular, S.HashVariant.NT1_32, want_minimizers=True)
+    assert g16.n_minimizers == g32.n_minimizers > 0
+    assert np.array_equal(g16.minimizers["hash"], g32.minimizers["hash"] & np.uint32(0xffff))
+    b16 = ctx.lib.c.s2k_bound_u16
+    assert b16(0.01) == 655 and b16(2.0) == 65535 and b16(-1.0) == 0 and b16(float("nan")) == 0
+    with pytest.raises(S.S2KError):                    # the SIMD iterators take a u32 bound
+        ctx.run(b1, so1, 10, 3, 0.01, S.HashMode.HpcSimd, V)

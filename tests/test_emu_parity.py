@@ -239,6 +239,12 @@ def test_h64_flavour_emulated(S, O, emu_ctx, batches, fixture_seq):
     check_h64_flavour(S, O, emu_ctx, batches, fixture_seq, scale=1)
 
 
+def test_h16_flavour_emulated(S, O, emu_ctx, batches, fixture_seq):
+    """H = u16 (parity unpinned): closed-form parity in the modes Hpc and Regular."""
+    from parity_cases import check_h16_flavour
+    check_h16_flavour(S, O, emu_ctx, batches, fixture_seq, scale=1)
+
+
 def test_kminmer_vec_flavour_emulated(S, O, emu_ctx, batches, fixture_seq):
     """KminmerVec (src/kminmer.rs:17-126) built from the minimizer stream: the same windows as the KminmerHash items
     (start, end, offset), canonical orientation by lexicographic order of the hash vector."""
@@ -258,3 +264,27 @@ def test_kminmer_vec_flavour_emulated(S, O, emu_ctx, batches, fixture_seq):
     assert a == r and a.rev != r.rev and a.mers() == [2, 1, 3] and a.print() == "2 1 3 "
     assert a.get_hash_u64() == r.get_hash_u64() != S.KminmerVec([2, 1, 4], 0, 9, 0).get_hash_u64()
     assert sorted([S.KminmerVec([5, 1], 0, 1, 0), S.KminmerVec([1, 2], 0, 1, 1)])[0].mers() == [1, 2]
+
+
+def test_minimizer_tsv_round_trip_emulated(S, O, emu_ctx, fixture_seq, tmp_path):
+    """src/old/kminmers-readwrite.rs: `{prefix}-{l}-{density}.mers` written from the device's minimizers, k-min-mers
+    rebuilt from the file alone; lines and items against the oracle's minimizers."""
+    seq = bytes(fixture_seq)[:40000]
+    for hpc, l, k, d in ((True, 31, 5, 0.01), (False, 12, 3, 0.02)):
+        prefix = str(tmp_path / ("hpc" if hpc else "reg"))
+        w = S.KminmersWriteIterator(seq, l, k, d, hpc, prefix, ctx=emu_ctx)
+        assert w.path == f"{prefix}-{l}-{d}.mers"
+        written = list(w)
+        read = list(S.KminmersReadIterator(l, k, d, prefix))
+        st, en, h = O.closed_profile(seq, l, d, 1 if hpc else 0)
+        lines = open(w.path).read().splitlines()
+        assert lines == [f"{int(p) + (0 if hpc else 1)}\t{int(x)}" for p, x in zip(st, h)] and len(lines) > 100
+        assert len(read) == len(written) == len(h) - k + 1
+        for c, (a, b) in enumerate(zip(written, read)):
+            assert a == b and (a.start, a.end, a.offset, a.rev) == (b.start, b.end, b.offset, b.rev)
+            assert a.offset == c and a.start == int(st[c]) + (0 if hpc else 1)
+            assert a.end == int(st[c + k - 1]) + (0 if hpc else 1) + l - 1
+            w5 = [int(x) for x in h[c:c + k]]
+            assert a.mers() == min(w5, w5[::-1])
+    assert S.mers_path("p", 31, 0.01) == "p-31-0.01.mers" and S.mers_path("p", 5, 1.0) == "p-5-1.mers"
+    assert S.mers_path("p", 5, 1e-7) == "p-5-0.0000001.mers" and S.mers_path("p", 5, 0.5) == "p-5-0.5.mers"

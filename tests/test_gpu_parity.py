@@ -347,6 +347,13 @@ def test_h64_flavour(S, O, gpu_ctx, batches, fixture_seq):
 
 
 @pytest.mark.gpu
+def test_h16_flavour(S, O, gpu_ctx, batches, fixture_seq):
+    """H = u16 (parity unpinned): closed-form parity in the modes Hpc and Regular."""
+    from parity_cases import check_h16_flavour
+    check_h16_flavour(S, O, gpu_ctx, batches, fixture_seq, scale=4)
+
+
+@pytest.mark.gpu
 def test_one_pass_per_run_at_baseline_densities(S, gpu_ctx):
     """run_device sizes its buffers from the expected selection rate and reruns a batch whose records overflow them.
     At BASELINE's densities that must not happen (HPC off at d = 0.01 once overflowed a per-CTA append region on every
