@@ -1819,8 +1819,14 @@ struct K3TArgs {
     const ulonglong2 *tile_src;
     uint32_t n_tiles;
 };
+// Six CTAs per SM (40 registers): with no minimum ptxas settles on 40 registers AND spills 12 bytes; 8 CTAs (32 registers)
+// and one-wave grids measured no better (profiles/r2_ab_log.txt: window stage 1.297 -> 1.265 ms on config 2).
+#ifndef S2K_WIN_MINB
+#define S2K_WIN_MINB 6
+#endif
+#define S2K_WIN_BOUNDS __launch_bounds__(256, S2K_WIN_MINB)
 template <int K>
-__global__ void __launch_bounds__(256) k_windows_t(const __grid_constant__ K3TArgs A)
+__global__ void S2K_WIN_BOUNDS k_windows_t(const __grid_constant__ K3TArgs A)
 {
     constexpr uint32_t OUT = 32 - (K - 1);
     if (*A.W.err & ERR_CAP) return;

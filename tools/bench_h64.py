@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Resident throughput of the H = u64 flavour (S2K_HASH_NT1_64, modes Hpc and Regular) on a config-2 shaped batch
+"""Resident throughput of the H = u64 and H = u16 flavours (S2K_HASH_NT1_64 / S2K_HASH_NT1_16, modes Hpc and Regular) on a config-2 shaped batch
 (reads x 20 kb, l=31 k=5 d=0.01), next to the 32-bit scalar-profile run of the same mode.  CUDA events on the stream.
 Usage (GPU box): python tools/bench_h64.py [reads]"""
 import os, sys
@@ -15,7 +15,7 @@ ctx.synth_device(0x5EED0002, 0, n, d_b.data_ptr())
 d_so = torch.arange(n_reads + 1, dtype=torch.int64, device="cuda:0") * read_len
 torch.cuda.synchronize()
 for mode in (S.HashMode.Hpc, S.HashMode.Regular):
-    for var in (S.HashVariant.NT1_32, S.HashVariant.NT1_64):
+    for var in (S.HashVariant.NT1_32, S.HashVariant.NT1_64, S.HashVariant.NT1_16):
         for _ in range(2):
             r = ctx.run_device(d_b.data_ptr(), d_so.data_ptr(), n_reads, n, 31, 5, 0.01, mode, var)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
