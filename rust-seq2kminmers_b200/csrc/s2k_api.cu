@@ -581,6 +581,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
         if (in_place) {
             K3TArgs D;
             D.W = C; D.tile_info = ptr<uint4>(ctx->d_tile_info); D.tile_src = B.tile_src; D.n_tiles = n_tiles;
+            // short reads (fewer than ~4k expected minimizers per sequence): most windows span two sequences
+            D.ridtest = (double)cap / (double)n_seqs < 4.0 * (double)P.k ? 1u : 0u;
             static const int win_bps = getenv("S2K_WIN_BPS") ? atoi(getenv("S2K_WIN_BPS")) : 16;
             const int g3 = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * win_bps);
             switch ((int)P.k) {

@@ -1037,6 +1037,23 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
         const int dlt = (int)((hk_real - (uint32_t)d) & 3u);
         const int hk = (int)hk_real - dlt;
         if (st16[0] | st16[1] | st16[2] | st16[3]) {       // sequence starts among this thread's kept bases -> owner-space flags
+#ifndef S2K_START_LOOP_PER_PIECE
+            // One loop over the starts of all four pieces: on 150-bp reads a thread holds 0.4 starts, some lane of every
+            // warp has one in every piece, and a loop per piece made each warp walk four divergent branches (3.9 of
+            // config 3's 36.3 instructions per base; profiles/r2_c3_phases.txt).
+            uint32_t s01 = (st16[0] & k16[0]) | ((st16[1] & k16[1]) << 16), s23 = (st16[2] & k16[2]) | ((st16[3] & k16[3]) << 16);
+            while (s01 | s23) {
+                const bool up = s01 == 0u;
+                const int b = __ffs((int)(up ? s23 : s01)) - 1;
+                if (up) s23 &= s23 - 1u; else s01 &= s01 - 1u;
+                const int hi = b >> 4, bb = b & 15, j = (up ? 2 : 0) + hi;
+                const uint32_t kj = up ? (hi ? k16[3] : k16[2]) : (hi ? k16[1] : k16[0]);
+                const uint32_t qq = up ? (hi ? qj[3] : qj[2]) : (hi ? qj[1] : qj[0]);
+                const uint32_t sh2 = S.shortw[64 * warp + 16 * j + (lane >> 1)] >> (16 * (lane & 1) + bb);
+                const int oo = (int)qq + __popc(kj & lowmask((uint32_t)bb)) - hk + XB;
+                if (oo >= 0) flag_owner(S, par, oo, sh2 & 1u);
+            }
+#else
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint32_t sw = st16[j] & k16[j];
@@ -1050,6 +1067,7 @@ __global__ void __launch_bounds__(NT, S2K_MINB) k_minimizers(const __grid_consta
                     }
                 }
             }
+#endif
         }
         // ---- S4b: not enough context in the halo -> walk back through the sequence (rare: long homopolymers)
         if (need_walk && warp == 0) {
@@ -1818,6 +1836,9 @@ struct K3TArgs {
     const uint4 *tile_info;
     const ulonglong2 *tile_src;
     uint32_t n_tiles;
+    uint32_t ridtest;               // 1: test that a window's first and last record share the sequence before the per-
+                                    // sequence loads (short reads; on long reads the extra shuffle costs more than it spares:
+                                    // config 3 window stage 3.73 -> 3.47 ms, config 2 1.265 -> 1.280 ms)
 };
 // Six CTAs per SM (40 registers): with no minimum ptxas settles on 40 registers AND spills 12 bytes; 8 CTAs (32 registers)
 // and one-wave grids measured no better (profiles/r2_ab_log.txt: window stage 1.297 -> 1.265 ms on config 2).
@@ -1851,7 +1872,10 @@ __global__ void S2K_WIN_BOUNDS k_windows_t(const __grid_constant__ K3TArgs A)
             uint64_t f = 0, r = 0;
             WindowFold<K, 0>::run(mix32(rec.x), f, r);
             const uint32_t end = K > 1 ? __shfl_down_sync(0xffffffffu, rec.z, K - 1) : rec.z;
-            if (lane < OUT && j < h) {
+            // a window lies inside one sequence: on short reads (config 3: 1.65 minimizers per read) this spares 98 % of
+            // the lanes the three dependent, scattered loads below (A.ridtest; the exact test follows either way)
+            const uint32_t rid_last = (K > 1 && A.ridtest) ? __shfl_down_sync(0xffffffffu, rec.w, K - 1) : rec.w;   // uniform
+            if (lane < OUT && j < h && rid_last == rec.w) {
                 const uint32_t rid = rec.w;
                 const uint64_t c = ts.x + j - A.W.min_off[rid];
                 const uint64_t k0 = A.W.km_off[rid];
