@@ -583,10 +583,10 @@ def run_b200(args):
     return 0 if (parity is None or parity.get("digest_match", True) or not parity.get("checked")) else 1
 
 
-# Figures of the committed ncu capture of the current k_minimizers (profiles/r2_final_kernel_summary.txt, 1.000 Gbp launch)
-NCU_SOURCE = "profiles/r2_final_kernel_summary.txt"
-NCU_DRAM_READ, NCU_DRAM_WRITE = 1.1004e9, 0.3086e9
-NCU_INSTR_PER_BASE, NCU_ALU_SHARE = 30.01, 0.529      # smsp__inst_executed; ALU-class share (profiles/r2_final_phases.txt)
+# Figures of the committed ncu capture of the current k_minimizers (profiles/r2_last_kernel_summary.txt, 1.000 Gbp launch)
+NCU_SOURCE = "profiles/r2_last_kernel_summary.txt"
+NCU_DRAM_READ, NCU_DRAM_WRITE = 1.1013e9, 0.3088e9
+NCU_INSTR_PER_BASE, NCU_ALU_SHARE = 29.87, 0.534      # smsp__inst_executed; ALU-class share (profiles/r2_last_phases.txt)
 
 
 def run_c5(B, O, args):
