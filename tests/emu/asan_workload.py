@@ -11,7 +11,7 @@ so = np.zeros(len(seqs) + 1, dtype=np.uint64); so[1:] = np.cumsum([len(s) for s 
 # exact-size buffers so that any over-read of the inputs is caught
 bases = bases.copy(); so = so.copy()
 ctx = S.Context(0, S.Library(os.environ['S2K_ASAN_LIB']))
-for mode, var, l in [(3, 0, 31), (1, 0, 31), (0, 0, 31), (3, 1, 31), (1, 0, 255), (3, 0, 1), (1, 2, 40)]:
+for mode, var, l in [(3, 0, 31), (1, 0, 31), (0, 0, 31), (3, 1, 31), (1, 0, 255), (3, 0, 1), (1, 2, 40), (1, 3, 31), (0, 3, 20)]:
     r = ctx.run(bases, so, l, 5, 0.05, S.HashMode(mode), S.HashVariant(var), want_minimizers=True)
     print("ok", mode, var, l, r.n_items)
 ctx.set_slab_bytes(30000)
