@@ -1858,6 +1858,16 @@ __global__ void S2K_WIN_BOUNDS k_windows_t(const __grid_constant__ K3TArgs A)
         const uint32_t h = A.tile_info[t].x;
         if (h == 0) continue;
         const ulonglong2 ts = A.tile_src[t];
+#if !defined(S2K_EMU) && !defined(S2K_WIN_NO_PREFETCH)
+        // The stage is latency-bound (one 512-byte load in flight per warp, long-scoreboard stalls 14 of 20 cycles per
+        // issue): pull the tile's records (~4 KB; the first 256 of them) into L2, one prefetch per 32-byte sector, so
+        // that the passes after the first wait for L2 instead of DRAM.  No register is held for it.
+#pragma unroll
+        for (uint32_t m = 0; m < 4; ++m) {
+            const uint32_t idx = 2u * lane + 64u * m;
+            if (idx < h) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.W.mins + ts.y + idx));
+        }
+#endif
         for (uint32_t p0 = 0; p0 < h; p0 += OUT) {
             const uint32_t j = p0 + lane;
             uint4 rec = make_uint4(0u, 0u, 0u, 0u);
