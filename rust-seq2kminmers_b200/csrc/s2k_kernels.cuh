@@ -1938,6 +1938,11 @@ __global__ void __launch_bounds__(NT) k_rle(const __grid_constant__ K4Args A)
     S2K_SHARED uint32_t wsum[NT / 32];
     S2K_SHARED uint32_t s_tile;
     S2K_SHARED unsigned long long s_excl;
+    // the tile's output, staged so that it leaves in whole sectors: a thread's ~24 kept bases are consecutive in the
+    // output but 24 bytes / 96 bytes away from its neighbours', and byte / word stores straight to global memory made
+    // every store instruction touch 32 sectors (148 Gbp/s; profiles/r2_rle.txt)
+    S2K_SHARED uint32_t s_pos[RLE_TILE];
+    S2K_SHARED uint32_t s_hpc[RLE_TILE / 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
         __syncthreads();
@@ -2023,17 +2028,33 @@ __global__ void __launch_bounds__(NT) k_rle(const __grid_constant__ K4Args A)
             while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (A.seq_off[mid] <= g0) lo = mid + 1; else hi = mid; }
             uint32_t rid = lo - 1;
             uint64_t so = A.seq_off[rid], nx = A.seq_off[rid + 1];
-            uint64_t o = base + q;
+            uint32_t o = q;
+            uint8_t *const sb = reinterpret_cast<uint8_t *>(s_hpc);
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
                 if ((keep >> b) & 1u) {
                     const uint64_t g = g0 + b;
                     while (g >= nx) { ++rid; so = A.seq_off[rid]; nx = A.seq_off[rid + 1]; }
-                    A.hpc[o] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
-                    A.pos[o] = (uint32_t)(g - so);
+                    sb[o] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+                    s_pos[o] = (uint32_t)(g - so);
                     ++o;
                 }
             }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < tot; i += NT) A.pos[base + i] = s_pos[i];
+        {   // kept bytes: the destination starts at any byte -- bytes up to a word boundary, whole words, bytes again
+            const uint8_t *const sb = reinterpret_cast<const uint8_t *>(s_hpc);
+            const uint32_t head = min(tot, (uint32_t)((4u - (uint32_t)(base & 3ull)) & 3u));
+            if ((uint32_t)tid < head) A.hpc[base + tid] = sb[tid];
+            const uint32_t nw = (tot - head) >> 2;
+            uint32_t *const dw = reinterpret_cast<uint32_t *>(A.hpc + base + head);
+            for (uint32_t i = tid; i < nw; i += NT) {
+                const uint32_t a = head + 4u * i, sh = 8u * (a & 3u);      // shared side: unaligned by `head`
+                dw[i] = __funnelshift_r(s_hpc[a >> 2], s_hpc[(a >> 2) + (sh ? 1u : 0u)], sh);
+            }
+            const uint32_t tail0 = head + 4u * nw;
+            if ((uint32_t)tid < tot - tail0) A.hpc[base + tail0 + tid] = sb[tail0 + tid];
         }
         for (uint32_t i = lb + tid; i < ub; i += NT) {
             const uint64_t s = A.seq_off[i];
