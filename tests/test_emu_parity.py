@@ -288,3 +288,26 @@ def test_minimizer_tsv_round_trip_emulated(S, O, emu_ctx, fixture_seq, tmp_path)
             assert a.mers() == min(w5, w5[::-1])
     assert S.mers_path("p", 31, 0.01) == "p-31-0.01.mers" and S.mers_path("p", 5, 1.0) == "p-5-1.mers"
     assert S.mers_path("p", 5, 1e-7) == "p-5-0.0000001.mers" and S.mers_path("p", 5, 0.5) == "p-5-0.5.mers"
+
+
+def test_hash_width_flavours_through_slabs_emulated(S, emu_ctx):
+    """H = u16 and H = u64 through the pipelined host path: slabs, a sequence cut into pieces, 2-bit transport -- the
+    same items and minimizers as the one-shot run."""
+    rng = np.random.default_rng(7)
+    lens = [0, 31, 150, 9000, 20000, 47, 120000, 3, 700, 64000]
+    seqs = [np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 4 if i % 3 else 5, n)] for i, n in enumerate(lens)]
+    so = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    so[1:] = np.cumsum(lens)
+    bases = np.concatenate(seqs)
+    try:
+        for var in (S.HashVariant.NT1_16, S.HashVariant.NT1_64):
+            for mode in (S.HashMode.Hpc, S.HashMode.Regular):
+                emu_ctx.set_slab_bytes(0)
+                a = emu_ctx.run(bases, so, 21, 4, 0.03, mode, var, want_minimizers=True)
+                emu_ctx.set_slab_bytes(30000)
+                b = emu_ctx.run(bases, so, 21, 4, 0.03, mode, var, want_minimizers=True)
+                assert a.n_items > 1000 and emu_ctx.last_transport()[2] > 1
+                for f in ("hash", "start", "end", "rev", "km_off", "min_off", "min_cnt", "minimizers"):
+                    assert np.array_equal(getattr(a, f), getattr(b, f)), (var, mode, f)
+    finally:
+        emu_ctx.set_slab_bytes(0)
