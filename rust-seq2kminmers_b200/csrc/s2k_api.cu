@@ -583,8 +583,8 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
             D.W = C; D.tile_info = ptr<uint4>(ctx->d_tile_info); D.tile_src = B.tile_src; D.n_tiles = n_tiles;
             // short reads (fewer than ~4k expected minimizers per sequence): most windows span two sequences
             D.ridtest = (double)cap / (double)n_seqs < 4.0 * (double)P.k ? 1u : 0u;
-            static const int win_bps = getenv("S2K_WIN_BPS") ? atoi(getenv("S2K_WIN_BPS")) : 16;
-            const int g3 = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * win_bps);
+            // 16 CTAs per SM in the grid (2.7 waves at six resident): one-wave grids measured slower, the tiles are uneven
+            const int g3 = (int)std::min<uint64_t>(((uint64_t)n_tiles + 7) / 8, (uint64_t)ctx->sm_count * 16);
             switch ((int)P.k) {
 #define S2K_WINDOWS_CASE(K) case K: S2K_LAUNCH(k_windows_t<K>, g3, 256, 0, st, false, D); break;
                 S2K_WINDOWS_CASE(1) S2K_WINDOWS_CASE(2) S2K_WINDOWS_CASE(3) S2K_WINDOWS_CASE(4) S2K_WINDOWS_CASE(5) S2K_WINDOWS_CASE(6)

@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B of the in-place window stage (k_windows_t): registers per thread (launch bounds) x blocks per SM in the grid.
+# (History: S2K_WIN_BPS was a temporary environment knob of run_device for this A/B; the grid is fixed at 16 CTAs per SM now.)
 mkdir -p gpurun_out
 line() { python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-parity --no-extra 2>/dev/null | tail -1 | python -c "
 import json,sys
