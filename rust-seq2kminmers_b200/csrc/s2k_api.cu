@@ -358,6 +358,15 @@ int make_plan(s2k_ctx *ctx, const s2k_params *p, Plan &P)
     return S2K_OK;
 }
 
+// Fraction of the hash space at or below the bound (capacity of the minimizer stream, overlap of the pieces of a long
+// sequence): the bound lives on 64 bits (H = u64), 16 bits (H = u16, mode Regular) or w bits.
+double selection_fraction(const Plan &P)
+{
+    if (P.h64) return std::min(1.0, ((double)P.thr64 + 1.0) / 18446744073709551616.0);
+    if (P.trunc16) return std::min(1.0, ((double)P.thr + 1.0) / 65536.0);
+    return std::min(1.0, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+}
+
 template <typename T> T *ptr(Buf &b) { return reinterpret_cast<T *>(b.p); }
 
 typedef void (*MinimizerKernel)(const K1Args);
@@ -439,8 +448,7 @@ int run_device(s2k_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_seq_off, 
     // capacity of the minimizer stream: expected 2*density*(kept bases), with head room; grown and rerun on overflow
     uint64_t cap;
     {
-        const double frac = P.h64 ? std::min(1.0, ((double)P.thr64 + 1.0) / 18446744073709551616.0)
-                                  : std::min(1.0, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+        const double frac = selection_fraction(P);
         double rate = std::min(1.0, 2.0 * frac) * 1.15 + 0.0005;
         rate = std::max(rate, ctx->rate_hint * 1.05);
         cap = std::min<uint64_t>(n_bases, (uint64_t)((double)n_bases * rate) + 65536);
@@ -1412,7 +1420,7 @@ static int run_host(s2k_ctx *ctx, const uint8_t *bases, const uint64_t *seq_off,
         if (n_bases > slab + slab / 2 && n_seqs >= 1) {
             // right overlap of a piece of a long sequence: room for k-1 further minimizers at the selection rate, with a
             // wide margin (checked per piece; grown and redone if some stretch of the sequence is poorer than that)
-            const double frac = std::max(1e-9, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+            const double frac = std::max(1e-9, selection_fraction(P));
             uint64_t overlap = (uint64_t)std::min(4.0e9, 64.0 * (P.k + 8.0) / frac + 64.0 * P.l + 4096.0);
             for (int attempt = 0; attempt < 3; ++attempt) {
                 int too_short = 0;
@@ -1578,7 +1586,7 @@ int s2k_run_fastx(s2k_ctx *ctx, const char *path, int nb_threads, const s2k_para
         ctx->err.clear();
         FxSource src;
         src.file = f.p; src.recs = all.data(); src.seq_off = ho; src.n_recs = n_seqs;
-        const double frac = std::max(1e-9, ((double)P.thr + 1.0) / (P.w31 ? 2147483648.0 : 4294967296.0));
+        const double frac = std::max(1e-9, selection_fraction(P));
         uint64_t overlap = (uint64_t)std::min(4.0e9, 64.0 * (P.k + 8.0) / frac + 64.0 * P.l + 4096.0);
         fx_lap("offsets built");
         for (int attempt = 0; attempt < 3; ++attempt) {
